@@ -1,0 +1,84 @@
+"""Pins the CPU oracle against every known answer the reference holds for the hot path.
+
+The reference has no hot-path tests; the only quantitative known answer is the
+README OOK walkthrough (README.md:112-187) on examples/cupboard-superdec.sr400.cf32, plus the
+qualitative config-1 picture (README.md:90-94, screenshots/fsk-5.png).
+"""
+import itertools
+import re
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+
+@pytest.fixture(scope="module")
+def cupboard(golden_dir):
+    return O.Samples.from_file(golden_dir / "cupboard-superdec.sr400.cf32", O.CF32, 400)
+
+
+def _bits(idx):
+    return "".join("." if (r == 0).all() else "X" for r in idx)
+
+
+def test_readme_ook_run_lengths(cupboard):
+    # README.md:113-116: sparkfft -width 4 -stride 2 -range 0.001:0.01
+    assert cupboard.len() == 1994 and cupboard.sample_rate() == 400
+    idx, _ = cupboard.spark_fft(4, 2, (0.001, 0.01))
+    assert idx.shape == (995, 4)
+    runs = [(k, len(list(g))) for k, g in itertools.groupby(_bits(idx))]
+    # README.md:135-140: " 8 . / 8 X / 16 . / 17 X / 15 . / 16 X"
+    want = [(".", 8), ("X", 8), (".", 16), ("X", 17), (".", 15), ("X", 16)]
+    assert any(runs[i : i + 6] == want for i in range(len(runs))), runs
+
+
+def test_readme_ook_bitstrings_and_temperature(cupboard):
+    idx, _ = cupboard.spark_fft(4, 2, (0.001, 0.01))
+    # the README pipes the header line through sed too, which becomes the leading X
+    bits = "X" + _bits(idx).replace(".", "o")
+    # README.md:160: sed -E 's/X{6,10}/A/g; s/o{5,10}/B/g'
+    ab = re.sub(r"o{5,10}", "B", re.sub(r"X{6,10}", "A", bits))
+    assert ab == ("XBBBBBBBBBBBBBBBBBBBBBBBBBBBBBABABABABABABBABAABABABBABAABABABABBAABABBABAABABBAABBAABABABABABABBAABB"
+                  "ABBBBBBBBBBBBBooo")  # README.md:161
+    # README.md:167-168
+    pairs = re.sub(r"(..)", r"\1_", re.sub(r".*BBBBABAB(AB)*BABA", "", ab))
+    assert pairs == ("AB_AB_AB_BA_BA_AB_AB_AB_AB_BA_AB_AB_BA_BA_AB_AB_BA_AB_BA_AB_AB_AB_AB_AB_AB_BA_AB_BA_"
+                     "BB_BB_BB_BB_BB_BB_Bo_oo_")
+    # README.md:174-175
+    out = re.sub(r"(.{8})(.)", r"\1^\2^", pairs.replace("AB_", "0").replace("BA_", "1"))
+    assert out.startswith("00011000^0^10011001^0^10000001^0^1")
+    assert 24 + 153 / 255 == pytest.approx(24.6, abs=1e-9)  # README.md:187
+
+
+def test_readme_text_format(cupboard):
+    txt = cupboard.spark_fft_text(4, 2, (0.001, 0.01))
+    lines = txt.split("\n")
+    assert lines[0] == "sparkfft sample_rate=400"  # fft.rs:19
+    assert len(lines) == 1 + 995 + 1 and lines[-1] == ""
+    assert lines[1] == "│    │"  # fft.rs:63
+    assert all(len(l) == 6 for l in lines[1:-1])
+
+
+def test_config1_fsk_structure(golden_dir):
+    # README.md:90-94 = BASELINE.json configs[0]
+    s = O.Samples.from_file(golden_dir / "fsk-example.sr21M.fc32", O.CF32, 21_000_000)
+    assert s.len() == 196_864
+    chain = s.shift(280_000).lowpass(200_000, decimate=32, size=400)
+    assert chain.len() == 1 + (196_864 - 400) // 32 == 6140
+    assert chain.sample_rate() == 21_000_000 // 32
+    O.set_kept_only(True)
+    try:
+        idx, mag = chain.spark_fft(64, 16)
+    finally:
+        O.set_kept_only(False)
+    assert idx.shape == (380, 64)
+    assert idx.max() <= 3 and mag.max() < 0.25
+    # two alternating FSK columns (screenshots/fsk-5.png): energy concentrates in two bin groups
+    col = (idx > 0).sum(axis=0)
+    hot = set(np.argsort(col)[-4:].tolist())
+    assert hot == {24, 25, 47, 48}, (hot, col)
+    # the two tones alternate: rows where the left group is lit rarely have the right group lit
+    left = (idx[:, 24:26] > 0).any(axis=1)
+    right = (idx[:, 47:49] > 0).any(axis=1)
+    assert (left ^ right).mean() > 0.8
