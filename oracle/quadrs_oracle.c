@@ -98,6 +98,8 @@ struct qo_samples {
     qo_samples *inner; /* owned, as Shift<S>{inner} / LowPass<S>{inner} own by value (shift.rs:7-11, filter.rs:14-19) */
     /* SampleFile, samples.rs:44-49 */
     const uint8_t *mem;
+    uint64_t mem_base_bytes; /* window source (tests only): mem[0] is byte mem_base_bytes of the capture */
+    uint64_t mem_bytes;
     int fd;
     uint64_t file_len;
     int format;
@@ -167,10 +169,24 @@ qo_samples *qo_from_mem(const uint8_t *data, uint64_t n_bytes, int format, uint6
     if (!s) return NULL;
     s->kind = K_FILE;
     s->mem = data;
+    s->mem_bytes = n_bytes;
     s->fd = -1;
     s->file_len = n_bytes;
     s->format = format;
     s->sample_rate = sample_rate;
+    return s;
+}
+
+/* Test helper, not in the reference: a capture of total_samples of which only the window
+ * [base_sample, base_sample + n_bytes/pair) is backed by memory.  Lets the oracle evaluate reads at
+ * absolute offsets near 2^33..2^34 without materialising 32..128 GiB. */
+qo_samples *qo_from_mem_window(const uint8_t *data, uint64_t n_bytes, int format, uint64_t sample_rate,
+                               uint64_t base_sample, uint64_t total_samples)
+{
+    qo_samples *s = qo_from_mem(data, n_bytes, format, sample_rate);
+    if (!s) return NULL;
+    s->mem_base_bytes = base_sample * pair_bytes(format);
+    s->file_len = total_samples * pair_bytes(format);
     return s;
 }
 
@@ -387,7 +403,12 @@ static size_t file_read_at(const qo_samples *s, uint64_t off, qo_cf32 *into, siz
         bytes = wanted_bytes < avail ? wanted_bytes : (size_t)avail;
         /* the reference allocates and fills a Vec<u8> per call (samples.rs:79-83) */
         tmp = xcalloc(wanted_bytes, 1);
-        memcpy(tmp, s->mem + off * pb, bytes);
+        if (off * pb < s->mem_base_bytes || off * pb + bytes > s->mem_base_bytes + s->mem_bytes) {
+            free(tmp);
+            qo_panic(QO_E_INVALID_ARG, "window source: bytes [%llu, +%zu) are not backed", (unsigned long long)(off * pb),
+                     bytes);
+        }
+        memcpy(tmp, s->mem + (off * pb - s->mem_base_bytes), bytes);
         src = tmp;
     } else {
         tmp = xcalloc(wanted_bytes, 1);

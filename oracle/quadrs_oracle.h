@@ -63,6 +63,8 @@ const char *qo_last_error(void);
 
 /* ---- graph construction (Operation::exec arms, src/lib.rs:89-121) ---- */
 qo_samples *qo_from_mem(const uint8_t *data, uint64_t n_bytes, int format, uint64_t sample_rate);
+qo_samples *qo_from_mem_window(const uint8_t *data, uint64_t n_bytes, int format, uint64_t sample_rate,
+                               uint64_t base_sample, uint64_t total_samples); /* test helper */
 qo_samples *qo_from_file(const char *path, int format, uint64_t sample_rate);
 int qo_gen(const int64_t *cos_hz, size_t n_cos, uint64_t sample_rate, double seconds, qo_samples **out);
 int qo_shift(qo_samples *inner, int64_t frequency, qo_samples **out);

@@ -1,0 +1,134 @@
+// qd_device_math.cuh -- device-side arithmetic that must reproduce the reference bit for bit.
+//
+// Every helper here uses the *_rn intrinsics, which nvcc never contracts into FMA, so the rounding
+// sequence is exactly the reference's (Rust never contracts either).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace qd {
+
+// ---- FileFormat::to_f32, lib.rs:241-255 ------------------------------------------------------
+// The divide must be the correctly rounded IEEE divide; multiplying by a reciprocal is not bit-exact.
+__device__ __forceinline__ float dec_s8(int v) { return __fdiv_rn(static_cast<float>(v), 127.0f); }
+__device__ __forceinline__ float dec_u8(unsigned v) { return __fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 127.5f); }
+__device__ __forceinline__ float dec_s16(int v) { return __fsub_rn(__fdiv_rn(static_cast<float>(v), 65535.0f), 32767.5f); }
+
+// One sample (I first, Q second: lib.rs:234-237) at index i of a raw byte stream.
+__device__ __forceinline__ float2 decode_sample(const uint8_t *__restrict__ raw, int fmt, uint64_t i)
+{
+    switch (fmt) {
+    case 0: { // cf32: little-endian bit copy (NaN payloads preserved)
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(raw) + i);
+        return v;
+    }
+    case 1: { // cs8
+        const char2 v = __ldg(reinterpret_cast<const char2 *>(raw) + i);
+        return make_float2(dec_s8(v.x), dec_s8(v.y));
+    }
+    case 2: { // cu8
+        const uchar2 v = __ldg(reinterpret_cast<const uchar2 *>(raw) + i);
+        return make_float2(dec_u8(v.x), dec_u8(v.y));
+    }
+    default: { // cs16
+        const short2 v = __ldg(reinterpret_cast<const short2 *>(raw) + i);
+        return make_float2(dec_s16(v.x), dec_s16(v.y));
+    }
+    }
+}
+
+// ---- cos/sin of an f64 phase, rounded to f32 (shift.rs:50, gen.rs:41) ---------------------------
+// theta is the reference's own f64 phase.  Reduction by 2 pi/256 is exact (the first FMA's result is
+// representable because |r| < 2^-5 while 2 pi/256 has its last bit at 2^-58); the table is
+// double-double, so the f64 result carries < 0.51 ulp before the final rounding to f32 -- the same
+// class of error as glibc's sin/cos, hence the same f32 except on ~2^-28 of inputs.
+__device__ __forceinline__ void sincos_f64(double theta, const double *__restrict__ tab, double &cd, double &sd)
+{
+    const double K = 40.743665431525205956834243423364;   // 256 / (2 pi)
+    const double C1 = 6.283185307179586 / 256.0;           // fl64(2 pi) / 256, exact scaling
+    const double C2 = 2.4492935982947064e-16 / 256.0;      // (2 pi - fl64(2 pi)) / 256
+    const double kd = rint(__dmul_rn(theta, K));
+    double r = fma(-kd, C1, theta);
+    r = fma(-kd, C2, r);
+    const long long ki = static_cast<long long>(kd);
+    const double2 *tp = reinterpret_cast<const double2 *>(tab) + 2 * (ki & 255);
+    const double2 tcos = __ldg(tp), tsin = __ldg(tp + 1);
+    const double4 t = make_double4(tcos.x, tcos.y, tsin.x, tsin.y); // {ch, cl, sh, sl}
+    const double r2 = __dmul_rn(r, r);
+    double ps = fma(r2, -1.0 / 5040.0, 1.0 / 120.0);
+    ps = fma(r2, ps, -1.0 / 6.0);
+    ps = fma(__dmul_rn(r, r2), ps, r); // sin r
+    double pc = fma(r2, -1.0 / 720.0, 1.0 / 24.0);
+    pc = fma(r2, pc, -0.5);
+    pc = __dmul_rn(r2, pc); // cos r - 1
+    double tc = fma(t.x, pc, t.y);
+    tc = fma(-t.z, ps, tc);
+    cd = __dadd_rn(t.x, tc);
+    double ts = fma(t.z, pc, t.w);
+    ts = fma(t.x, ps, ts);
+    sd = __dadd_rn(t.z, ts);
+}
+
+__device__ __forceinline__ float2 phasor_exact(uint64_t n, double ratio, const double *__restrict__ tab)
+{
+    // shift.rs:49: (off + i) as f64 * self.ratio
+    const double place = __dmul_rn(__ull2double_rn(n), ratio);
+    double c, s;
+    sincos_f64(place, tab, c, s);
+    return make_float2(static_cast<float>(c), static_cast<float>(s));
+}
+
+// buf[i] *= mul  (num-complex 0.4.6 MulAssign): re' = re*c - im*s ; im' = im*c + re*s
+__device__ __forceinline__ float2 cmul_exact(float2 a, float2 m)
+{
+    return make_float2(__fsub_rn(__fmul_rn(a.x, m.x), __fmul_rn(a.y, m.y)),
+                       __fadd_rn(__fmul_rn(a.y, m.x), __fmul_rn(a.x, m.y)));
+}
+
+// Complex * Complex as num-complex Mul: (ar*br - ai*bi, ar*bi + ai*br) -- used by the FFT twiddles.
+__device__ __forceinline__ float2 cmul_tw(float2 a, float2 b)
+{
+    return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)),
+                       __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(__fsub_rn(a.x, b.x), __fsub_rn(a.y, b.y)); }
+
+// One radix-4 DIT butterfly of our FFT definition (see oracle/quadrs_oracle.c fft_rec):
+// inputs already twiddled; outputs X[k], X[k+q], X[k+2q], X[k+3q].
+__device__ __forceinline__ void radix4(float2 &t0, float2 &t1, float2 &t2, float2 &t3)
+{
+    const float2 s0 = cadd(t0, t2), s1 = csub(t0, t2), s2 = cadd(t1, t3), s3 = csub(t1, t3);
+    t0 = cadd(s0, s2);
+    t1 = make_float2(__fadd_rn(s1.x, s3.y), __fsub_rn(s1.y, s3.x)); // s1 - i*s3
+    t2 = csub(s0, s2);
+    t3 = make_float2(__fsub_rn(s1.x, s3.y), __fadd_rn(s1.y, s3.x)); // s1 + i*s3
+}
+
+// Complex::norm = re.hypot(im) -> glibc hypotf = (float)sqrt((double)x*x + (double)y*y) with the
+// inf/nan preamble of sysdeps/ieee754/flt-32/e_hypotf.c.  The f64 products are exact.
+__device__ __forceinline__ float hypot_exact(float x, float y)
+{
+    if (!isfinite(x) || !isfinite(y)) {
+        if (isinf(x) || isinf(y)) return __int_as_float(0x7f800000);
+        return x + y;
+    }
+    const double a = x, b = y;
+    return static_cast<float>(__dsqrt_rn(__dadd_rn(__dmul_rn(a, a), __dmul_rn(b, b))));
+}
+
+// fft.rs:53-60.  Returns 0..8, or 9 where the reference would index graph[7] and panic.
+__device__ __forceinline__ int glyph_index(float norm, float mn, float mx, float distinction)
+{
+    if (norm < mn) return 0;
+    if (norm >= mx) return 8;
+    const float q = __fdiv_rn(__fsub_rn(norm, mn), distinction);
+    if (!(q > 0.0f)) return 1; // `as usize` saturates NaN / negatives to 0
+    if (q >= 7.0f) return 9;
+    return 1 + static_cast<int>(q);
+}
+
+} // namespace qd

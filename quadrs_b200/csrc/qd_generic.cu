@@ -1,0 +1,662 @@
+// qd_generic.cu -- the general ("unit-local") executor: any chain, any order of stages.
+//
+// A sink unit is one top-level Samples::read_at(off, n) of the reference: a sparkfft window
+// (fft.rs:29-30), a do_write chunk (lib.rs:201-202), a take_fft row (ffts.rs:62) or a caller's own
+// read_at.  Each unit is evaluated exactly as the reference evaluates it -- every stage sees the
+// (off, n) its outer stage would have issued (filter.rs:68-71), including the zero-truncated filter
+// tail at the end of each LowPass::read_at buffer (filter.rs:107-124) -- but all units of a batch
+// run in parallel and every stage is a kernel over [units x samples].  This path is the semantic
+// ground truth on the GPU; qd_fast.cu holds the fused kernels for the canonical chains.
+#include <algorithm>
+#include <cstring>
+
+#include <unistd.h>
+
+#include "qd_device_math.cuh"
+#include "qd_internal.h"
+
+namespace qd {
+
+// ------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ uint64_t unit_off_top(uint64_t off0, uint64_t stride, const uint64_t *__restrict__ offsets,
+                                                 uint64_t u)
+{
+    return offsets ? offsets[u] : off0 + u * stride;
+}
+
+// valid[level * B + u] = samples the reference's read_at returns at that level for unit u
+__global__ void gk_geometry(GPlan p, uint64_t off0, uint64_t stride, const uint64_t *__restrict__ offsets, uint32_t B,
+                            uint32_t *__restrict__ valid)
+{
+    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= B) return;
+    const uint64_t o = unit_off_top(off0, stride, offsets, u) * p.mult[0];
+    uint64_t v;
+    if (p.src_kind == QD_SRC_GEN) v = p.n_level[0];            // gen.rs:36,46: always fills the buffer
+    else v = o < p.src_total ? min(p.n_level[0], p.src_total - o) : 0; // samples.rs:80-93
+    valid[u] = static_cast<uint32_t>(v);
+    for (int s = 0; s < p.n_stages; s++) {
+        if (p.st[s].kind == QD_STAGE_LOWPASS) v = v >= p.st[s].L ? (v - p.st[s].L) / p.st[s].D : 0; // filter.rs:76
+        valid[static_cast<size_t>(s + 1) * B + u] = static_cast<uint32_t>(v);
+    }
+}
+
+// Gen::read_at, gen.rs:36-44
+__device__ __forceinline__ float2 gen_sample(const GPlan &p, uint64_t n)
+{
+    const double tau = 6.283185307179586; // PI * 2.
+    const double base = __ddiv_rn(__dmul_rn(__ull2double_rn(n), tau), __ull2double_rn(p.src_rate));
+    float2 val = make_float2(0.0f, 0.0f);
+    for (int t = 0; t < p.n_tones; t++) {
+        const double f = __dmul_rn(__ll2double_rn(p.tones[t]), base);
+        double c, s;
+        sincos_f64(f, p.sincos, c, s);
+        val.x = __fadd_rn(val.x, static_cast<float>(c));
+        val.y = __fadd_rn(val.y, static_cast<float>(s));
+    }
+    return val;
+}
+
+// level 0: SampleFile::read_at / Gen::read_at, with the shifts that directly follow the source
+// applied in the same pass (Shift::read_at, shift.rs:46-54)
+__global__ void gk_source(GPlan p, int n_lead_shifts, uint64_t off0, uint64_t stride,
+                          const uint64_t *__restrict__ offsets, uint32_t B, const uint32_t *__restrict__ valid,
+                          float2 *__restrict__ out, uint32_t blocks_per_unit)
+{
+    const uint32_t u = blockIdx.x / blocks_per_unit;
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x % blocks_per_unit) * blockDim.x + threadIdx.x;
+    const uint64_t n0 = p.n_level[0];
+    if (u >= B || i >= n0) return;
+    float2 v = make_float2(0.0f, 0.0f); // the reference's buffers start zeroed
+    if (i < valid[u]) {
+        const uint64_t n = unit_off_top(off0, stride, offsets, u) * p.mult[0] + i;
+        v = p.src_kind == QD_SRC_GEN ? gen_sample(p, n) : decode_sample(p.src, p.fmt, n - p.src_base);
+        for (int s = 0; s < n_lead_shifts; s++) v = cmul_exact(v, phasor_exact(n, p.st[s].ratio, p.sincos));
+    }
+    out[static_cast<size_t>(u) * n0 + i] = v;
+}
+
+// a Shift that follows a LowPass: in place on its level
+__global__ void gk_shift(GPlan p, int stage, uint64_t off0, uint64_t stride, const uint64_t *__restrict__ offsets,
+                         uint32_t B, const uint32_t *__restrict__ valid, float2 *__restrict__ buf,
+                         uint32_t blocks_per_unit)
+{
+    const int level = stage + 1;
+    const uint32_t u = blockIdx.x / blocks_per_unit;
+    const uint64_t i = static_cast<uint64_t>(blockIdx.x % blocks_per_unit) * blockDim.x + threadIdx.x;
+    if (u >= B || i >= valid[static_cast<size_t>(level) * B + u]) return;
+    const uint64_t n = unit_off_top(off0, stride, offsets, u) * p.mult[level] + i;
+    float2 *q = buf + static_cast<size_t>(u) * p.n_level[level] + i;
+    *q = cmul_exact(*q, phasor_exact(n, p.st[stage].ratio, p.sincos));
+}
+
+// LowPass::read_at, filter.rs:54-83, kept outputs only:
+//   y[k] = sum_{j < min(L, valid_in - k*D - i0)} raw[k*D + i0 + j] * f[j],  i0 = L - L/2,
+// ascending j, multiply then add, each rounded (filter.rs:112-120; convoluted[L + k*D], :78-80).
+__global__ void gk_lowpass(GPlan p, int stage, uint32_t B, const uint32_t *__restrict__ valid,
+                           const float2 *__restrict__ in, float2 *__restrict__ out, uint32_t blocks_per_unit)
+{
+    const uint32_t u = blockIdx.x / blocks_per_unit;
+    const uint64_t k = static_cast<uint64_t>(blockIdx.x % blocks_per_unit) * blockDim.x + threadIdx.x;
+    const uint64_t n_in = p.n_level[stage], n_out = p.n_level[stage + 1];
+    if (u >= B || k >= n_out) return;
+    float2 acc = make_float2(0.0f, 0.0f);
+    if (k < valid[static_cast<size_t>(stage + 1) * B + u]) {
+        const uint32_t L = p.st[stage].L;
+        const uint64_t base = k * p.st[stage].D + (L - L / 2);
+        const uint64_t v_in = valid[static_cast<size_t>(stage) * B + u];
+        const uint32_t J = static_cast<uint32_t>(min(static_cast<uint64_t>(L), v_in - base));
+        const float2 *x = in + static_cast<size_t>(u) * n_in + base;
+        const float *__restrict__ f = p.st[stage].taps;
+        for (uint32_t j = 0; j < J; j++) {
+            const float2 s = x[j];
+            const float t = __ldg(f + j);
+            acc.x = __fadd_rn(acc.x, __fmul_rn(s.x, t));
+            acc.y = __fadd_rn(acc.y, __fmul_rn(s.y, t));
+        }
+    }
+    out[static_cast<size_t>(u) * n_out + k] = acc;
+}
+
+// ---- FFT of one unit per CTA in shared memory: our radix-4 DIT definition -------------------
+// Leaf position of natural index n: radix-4 digits of n, least significant first, become the most
+// significant digits of the position; a leftover top bit (odd log2 W) is the position's bit 0.
+__device__ __forceinline__ uint32_t leaf_position(uint32_t n, uint32_t W, int n_r4, bool odd)
+{
+    uint32_t p = 0, span = W;
+    for (int d = 0; d < n_r4; d++) {
+        span >>= 2;
+        p += (n & 3u) * span;
+        n >>= 2;
+    }
+    if (odd) p += n & 1u;
+    return p;
+}
+
+enum { EPI_SPARK = 0, EPI_LEVELS = 1, EPI_TAKE = 2 };
+
+struct FftArgs {
+    const float2 *in;     // [units][in_pitch] rows of W samples
+    uint64_t in_pitch;
+    const float2 *tw;     // w(W, j), j < W
+    const float *window;  // nullable (take_fft BlackmanHarris)
+    uint32_t W;
+    int epi;
+    float mn, mx, distinction;
+    uint8_t *idx;         // SPARK [units][W]; LEVELS [units]
+    float *mag;           // SPARK nullable / TAKE [units][W]
+    int *panic_flag;
+};
+
+__global__ void gk_fft(FftArgs a)
+{
+    extern __shared__ float2 x[];
+    const uint32_t W = a.W;
+    const uint32_t u = blockIdx.x;
+    int logw = 31 - __clz(W);
+    const bool odd = logw & 1;
+    const int n_r4 = logw >> 1;
+    const float2 *row = a.in + static_cast<size_t>(u) * a.in_pitch;
+    for (uint32_t n = threadIdx.x; n < W; n += blockDim.x) {
+        float2 v = row[n];
+        if (a.window) { // ffts.rs:64-68: Complex<f32> *= f32
+            const float w = a.window[n];
+            v = make_float2(__fmul_rn(v.x, w), __fmul_rn(v.y, w));
+        }
+        x[leaf_position(n, W, n_r4, odd)] = v;
+    }
+    __syncthreads();
+    if (odd) { // innermost size-2 FFTs
+        for (uint32_t b = threadIdx.x; b < W / 2; b += blockDim.x) {
+            const float2 p = x[2 * b], q = x[2 * b + 1];
+            x[2 * b] = cadd(p, q);
+            x[2 * b + 1] = csub(p, q);
+        }
+        __syncthreads();
+    }
+    for (uint32_t q = odd ? 2 : 1; q < W; q <<= 2) {
+        const uint32_t scale = W / (4 * q); // w(4q, j) == w(W, j * W/(4q))
+        for (uint32_t b = threadIdx.x; b < W / 4; b += blockDim.x) {
+            const uint32_t blk = b / q, k = b - blk * q;
+            float2 *base = x + static_cast<size_t>(blk) * 4 * q + k;
+            float2 t0 = base[0], t1 = base[q], t2 = base[2 * q], t3 = base[3 * q];
+            if (k != 0) {
+                t1 = cmul_tw(t1, __ldg(a.tw + k * scale));
+                t2 = cmul_tw(t2, __ldg(a.tw + 2 * k * scale));
+                t3 = cmul_tw(t3, __ldg(a.tw + 3 * k * scale));
+            }
+            radix4(t0, t1, t2, t3);
+            base[0] = t0;
+            base[q] = t1;
+            base[2 * q] = t2;
+            base[3 * q] = t3;
+        }
+        __syncthreads();
+    }
+    if (a.epi == EPI_LEVELS) { // fft.rs:95-97: sequential f32 sums over the natural-order halves
+        if (threadIdx.x < 2) {
+            const uint32_t lo = threadIdx.x ? W / 2 : 0, hi = threadIdx.x ? W : W / 2;
+            float s = 0.0f;
+            for (uint32_t b = lo; b < hi; b++) s = __fadd_rn(s, hypot_exact(x[b].x, x[b].y));
+            reinterpret_cast<float *>(x + W)[threadIdx.x] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const float *s = reinterpret_cast<float *>(x + W);
+            a.idx[u] = s[0] < s[1] ? 0 : 1;
+        }
+        return;
+    }
+    const uint32_t half = W / 2;
+    for (uint32_t b = threadIdx.x; b < W; b += blockDim.x) {
+        // iter().skip(w/2).chain(iter().take(w/2)), fft.rs:48-52 / ffts.rs:72-76
+        const uint32_t src = b < W - half ? b + half : b - (W - half);
+        const float norm = hypot_exact(x[src].x, x[src].y);
+        const size_t o = static_cast<size_t>(u) * W + b;
+        if (a.mag) a.mag[o] = norm;
+        if (a.epi == EPI_SPARK) {
+            const int g = glyph_index(norm, a.mn, a.mx, a.distinction);
+            if (g == 9) *a.panic_flag = 1;
+            a.idx[o] = static_cast<uint8_t>(g);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host orchestration
+// ------------------------------------------------------------------------------------------
+
+Chain::~Chain()
+{
+    if (src.fd >= 0) close(src.fd);
+    src.fd = -1;
+    if (!ctx) return; // description-only chain (qd_shard_plan): nothing lives on a device
+    cudaSetDevice(device);
+    auto rel = [](Buf &b) {
+        if (b.p) cudaFree(b.p);
+        b.p = nullptr;
+        b.cap = 0;
+    };
+    rel(stage_in);
+    for (auto &l : level) rel(l);
+    rel(geo);
+    rel(sink_a);
+    rel(sink_b);
+    rel(offsets);
+    rel(twiddles);
+    rel(window);
+    for (auto &s : stages)
+        if (s.d_taps) cudaFree(s.d_taps);
+    if (h_pinned) cudaFreeHost(h_pinned);
+    for (auto &e : prof_events) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
+    if (own_stream && stream) cudaStreamDestroy(stream);
+}
+
+int Chain::prof_begin()
+{
+    if (!profile) return QD_OK;
+    if (prof_used == prof_events.size()) {
+        cudaEvent_t a, b;
+        QD_CUDA(cudaEventCreate(&a));
+        QD_CUDA(cudaEventCreate(&b));
+        prof_events.emplace_back(a, b);
+    }
+    QD_CUDA(cudaEventRecord(prof_events[prof_used].first, stream));
+    return QD_OK;
+}
+
+int Chain::prof_end(const char *kernel)
+{
+    if (!profile) return QD_OK;
+    QD_CUDA(cudaEventRecord(prof_events[prof_used].second, stream));
+    prof_used++;
+    prof_kernel = kernel;
+    return QD_OK;
+}
+
+int Chain::ensure(Buf &b, size_t bytes)
+{
+    if (bytes <= b.cap) return QD_OK;
+    if (b.p) {
+        QD_CUDA(cudaStreamSynchronize(stream));
+        QD_CUDA(cudaFree(b.p));
+        b.p = nullptr;
+        b.cap = 0;
+    }
+    const size_t want = std::max(bytes, size_t(4096));
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return set_error(QD_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.cap = want;
+    return QD_OK;
+}
+
+int Chain::ensure_pinned(size_t bytes)
+{
+    if (bytes <= h_pinned_cap) return QD_OK;
+    if (h_pinned) {
+        QD_CUDA(cudaStreamSynchronize(stream));
+        QD_CUDA(cudaFreeHost(h_pinned));
+        h_pinned = nullptr;
+        h_pinned_cap = 0;
+    }
+    QD_CUDA(cudaMallocHost(&h_pinned, bytes));
+    h_pinned_cap = bytes;
+    return QD_OK;
+}
+
+// ---- the reference's count arithmetic, on the host ----
+
+int chain_len(const Chain &c, uint64_t *len)
+{
+    uint64_t v = c.src.kind == QD_SRC_GEN
+                     ? f64_as_u64(c.src.gen_seconds * static_cast<double>(c.src.sample_rate)) // gen.rs:31-33
+                     : c.src.total_samples;                                                    // samples.rs:64-66
+    for (const Stage &s : c.stages) {
+        if (s.kind != QD_STAGE_LOWPASS) continue; // shift.rs:38-40
+        if (!(v >= s.size))                       // filter.rs:46
+            return set_error(QD_E_SHORT_INPUT, "assertion failed: self.inner.len() >= self.filter.len() as u64");
+        v = 1 + (v - s.size) / s.decimate; // filter.rs:47
+    }
+    *len = v;
+    return QD_OK;
+}
+
+uint64_t chain_rate(const Chain &c)
+{
+    uint64_t r = c.src.sample_rate;
+    for (const Stage &s : c.stages)
+        if (s.kind == QD_STAGE_LOWPASS) r = r / s.decimate; // filter.rs:50-52
+    return r;
+}
+
+static void level_geometry(const Chain &c, uint64_t unit_len, uint64_t *n_level, uint64_t *mult)
+{
+    const int S = static_cast<int>(c.stages.size());
+    n_level[S] = unit_len;
+    mult[S] = 1;
+    for (int s = S - 1; s >= 0; s--) {
+        const Stage &st = c.stages[s];
+        if (st.kind == QD_STAGE_LOWPASS) { // filter.rs:68-71
+            n_level[s] = n_level[s + 1] * st.decimate + st.size;
+            mult[s] = mult[s + 1] * st.decimate;
+        } else {
+            n_level[s] = n_level[s + 1];
+            mult[s] = mult[s + 1];
+        }
+    }
+}
+
+int chain_valid(const Chain &c, uint64_t off, uint64_t n, uint64_t *valid)
+{
+    uint64_t n_level[kMaxStages + 1], mult[kMaxStages + 1];
+    level_geometry(c, n, n_level, mult);
+    uint64_t v;
+    if (c.src.kind == QD_SRC_GEN) {
+        v = n_level[0];
+    } else {
+        const uint64_t o = off * mult[0];
+        if (!(o < c.src.total_samples)) // samples.rs:74
+            return set_error(QD_E_OFFSET_EOF, "assertion failed: off < self.len() (off %llu, len %llu)",
+                             (unsigned long long)o, (unsigned long long)c.src.total_samples);
+        v = std::min(n_level[0], c.src.total_samples - o);
+    }
+    for (const Stage &s : c.stages) {
+        if (s.kind != QD_STAGE_LOWPASS) continue;
+        if (v < s.size) // filter.rs:76: usize underflow -> panic
+            return set_error(QD_E_SHORT_INPUT, "attempt to subtract with overflow (valid %llu < filter %llu)",
+                             (unsigned long long)v, (unsigned long long)s.size);
+        v = (v - s.size) / s.decimate;
+    }
+    *valid = v;
+    return QD_OK;
+}
+
+void chain_source_span(const Chain &c, uint64_t off, uint64_t n, uint64_t *lo, uint64_t *hi)
+{
+    uint64_t n_level[kMaxStages + 1], mult[kMaxStages + 1];
+    level_geometry(c, n, n_level, mult);
+    const uint64_t total = c.src.total_samples;
+    *lo = std::min(off * mult[0], total);
+    *hi = std::min(off * mult[0] + n_level[0], total);
+}
+
+static int fill_plan(Chain &c, uint64_t unit_len, GPlan *p)
+{
+    memset(p, 0, sizeof *p);
+    const int S = static_cast<int>(c.stages.size());
+    p->n_stages = S;
+    p->src_kind = c.src.kind;
+    p->fmt = c.src.format;
+    level_geometry(c, unit_len, p->n_level, p->mult);
+    for (int l = 0; l <= S; l++)
+        if (p->n_level[l] >= (uint64_t(1) << 31))
+            return set_error(QD_E_INVALID_ARG, "read of %llu samples needs %llu samples at level %d: too large",
+                             (unsigned long long)unit_len, (unsigned long long)p->n_level[l], l);
+    for (int s = 0; s < S; s++) {
+        const Stage &st = c.stages[s];
+        p->st[s].kind = st.kind;
+        p->st[s].L = static_cast<uint32_t>(st.size);
+        p->st[s].D = st.decimate;
+        p->st[s].ratio = st.ratio;
+        p->st[s].taps = st.d_taps;
+    }
+    p->src_total = c.src.total_samples;
+    p->src_rate = c.src.sample_rate;
+    p->n_tones = static_cast<int>(c.src.gen_cos.size());
+    for (int t = 0; t < p->n_tones; t++) p->tones[t] = c.src.gen_cos[t];
+    p->sincos = c.ctx->d_sincos;
+    return QD_OK;
+}
+
+// Makes raw samples [lo, hi) available on the device; sets plan->src / src_base.
+static int stage_source(Chain &c, uint64_t lo, uint64_t hi, GPlan *p)
+{
+    const Source &s = c.src;
+    if (s.kind == QD_SRC_GEN || hi <= lo) {
+        p->src = nullptr;
+        p->src_base = 0;
+        return QD_OK;
+    }
+    const uint64_t pb = pair_bytes(s.format);
+    if (lo < s.base_sample || hi > s.base_sample + s.resident_samples)
+        return set_error(QD_E_NOT_RESIDENT, "samples [%llu, %llu) requested but this source holds [%llu, %llu)",
+                         (unsigned long long)lo, (unsigned long long)hi, (unsigned long long)s.base_sample,
+                         (unsigned long long)(s.base_sample + s.resident_samples));
+    if (s.kind == QD_SRC_DEVICE_MEM) {
+        p->src = s.data;
+        p->src_base = s.base_sample;
+        return QD_OK;
+    }
+    const size_t bytes = static_cast<size_t>((hi - lo) * pb);
+    QD_TRY(c.ensure(c.stage_in, bytes));
+    if (s.kind == QD_SRC_HOST_MEM) {
+        QD_CUDA(cudaMemcpyAsync(c.stage_in.p, s.data + (lo - s.base_sample) * pb, bytes, cudaMemcpyHostToDevice,
+                                c.stream));
+    } else { // FILE: one pread per staged range, as SampleFile::read_at does per call (samples.rs:80-83)
+        QD_TRY(c.ensure_pinned(bytes));
+        QD_CUDA(cudaStreamSynchronize(c.stream)); // the pinned buffer may still feed an earlier copy
+        size_t done = 0;
+        while (done < bytes) {
+            const ssize_t r = pread(s.fd, static_cast<uint8_t *>(c.h_pinned) + done, bytes - done,
+                                    static_cast<off_t>(lo * pb + done));
+            if (r < 0) return set_error(QD_E_IO, "read %s: %s", s.path.c_str(), strerror(errno));
+            if (r == 0) return set_error(QD_E_IO, "read %s: unexpected end of file", s.path.c_str());
+            done += static_cast<size_t>(r);
+        }
+        QD_CUDA(cudaMemcpyAsync(c.stage_in.p, c.h_pinned, bytes, cudaMemcpyHostToDevice, c.stream));
+    }
+    p->src = static_cast<const uint8_t *>(c.stage_in.p);
+    p->src_base = lo;
+    return QD_OK;
+}
+
+static int ensure_twiddles(Chain &c, size_t W)
+{
+    if (c.twiddles_n == W) return QD_OK;
+    std::vector<float> tw(2 * W);
+    fft_twiddles(W, tw.data());
+    QD_TRY(c.ensure(c.twiddles, 2 * W * sizeof(float)));
+    QD_CUDA(cudaMemcpyAsync(c.twiddles.p, tw.data(), 2 * W * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    QD_CUDA(cudaStreamSynchronize(c.stream)); // tw is a stack-lifetime host vector
+    c.twiddles_n = W;
+    return QD_OK;
+}
+
+static int ensure_window(Chain &c, size_t W)
+{
+    if (c.window_n == W) return QD_OK;
+    std::vector<float> w(W);
+    blackman_harris(W, w.data());
+    QD_TRY(c.ensure(c.window, W * sizeof(float)));
+    QD_CUDA(cudaMemcpyAsync(c.window.p, w.data(), W * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    QD_CUDA(cudaStreamSynchronize(c.stream));
+    c.window_n = W;
+    return QD_OK;
+}
+
+static int copy_out(Chain &c, void *dst, const void *src, size_t bytes, int space)
+{
+    if (!bytes) return QD_OK;
+    QD_CUDA(cudaMemcpyAsync(dst, src, bytes, space == QD_SPACE_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                            c.stream));
+    return QD_OK;
+}
+
+int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets, uint64_t n_units, uint64_t unit_len,
+              SinkArgs &sink, uint64_t *n_out)
+{
+    if (n_out) *n_out = 0;
+    if (n_units == 0 || unit_len == 0) return QD_OK;
+    QD_CUDA(cudaSetDevice(c.device));
+    GPlan plan;
+    QD_TRY(fill_plan(c, unit_len, &plan));
+    const int S = plan.n_stages;
+    const size_t W = sink.width;
+    const bool fft_sink = sink.kind != SINK_SAMPLES;
+    if (fft_sink) {
+        if (W != unit_len) return set_error(QD_E_INVALID_ARG, "internal: fft sink width != unit length");
+        if (W * sizeof(float2) + 16 > 200 * 1024)
+            return set_error(QD_E_INVALID_ARG, "fft width %zu exceeds the supported maximum of 16384", W);
+        QD_TRY(ensure_twiddles(c, W));
+        if (sink.windowed) QD_TRY(ensure_window(c, W));
+    }
+
+    // leading shifts ride along with the source kernel
+    int n_lead = 0;
+    while (n_lead < S && plan.st[n_lead].kind == QD_STAGE_SHIFT) n_lead++;
+
+    // scratch per unit: one buffer per level, shift levels alias their input level
+    size_t per_unit = 0;
+    for (int l = 0; l <= S; l++)
+        if (l == 0 || plan.st[l - 1].kind == QD_STAGE_LOWPASS) per_unit += plan.n_level[l] * sizeof(float2);
+    if (fft_sink) per_unit += W * (sizeof(uint8_t) + sizeof(float));
+    uint64_t B = std::max<uint64_t>(1, c.scratch_budget / std::max<size_t>(per_unit, 1));
+    B = std::min<uint64_t>(B, std::min<uint64_t>(n_units, 32768));
+
+    Chain::Buf *lvl[kMaxStages + 1];
+    for (int l = 0; l <= S; l++) {
+        if (l == 0 || plan.st[l - 1].kind == QD_STAGE_LOWPASS) {
+            QD_TRY(c.ensure(c.level[l], B * plan.n_level[l] * sizeof(float2)));
+            lvl[l] = &c.level[l];
+        } else {
+            lvl[l] = lvl[l - 1];
+        }
+    }
+    QD_TRY(c.ensure(c.geo, B * (S + 1) * sizeof(uint32_t) + sizeof(int)));
+    int *d_panic = reinterpret_cast<int *>(static_cast<uint8_t *>(c.geo.p) + B * (S + 1) * sizeof(uint32_t));
+    if (fft_sink) {
+        QD_TRY(c.ensure(c.sink_a, B * (sink.kind == SINK_LEVELS ? 1 : W)));
+        if (sink.kind == SINK_TAKE || sink.mag_out) QD_TRY(c.ensure(c.sink_b, B * W * sizeof(float)));
+        QD_CUDA(cudaMemsetAsync(d_panic, 0, sizeof(int), c.stream));
+    }
+    if (offsets) QD_TRY(c.ensure(c.offsets, B * sizeof(uint64_t)));
+
+    uint64_t produced = 0;
+    std::vector<uint64_t> vcount;
+    for (uint64_t u0 = 0; u0 < n_units; u0 += B) {
+        const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(B, n_units - u0));
+        const uint64_t boff = off0 + u0 * stride;
+
+        // raw span of the batch
+        uint64_t lo = UINT64_MAX, hi = 0;
+        if (offsets) {
+            for (uint32_t i = 0; i < b; i++) {
+                uint64_t a, z;
+                chain_source_span(c, offsets[u0 + i], unit_len, &a, &z);
+                lo = std::min(lo, a);
+                hi = std::max(hi, z);
+            }
+            QD_CUDA(cudaMemcpyAsync(c.offsets.p, offsets + u0, b * sizeof(uint64_t), cudaMemcpyHostToDevice, c.stream));
+            QD_CUDA(cudaStreamSynchronize(c.stream));
+        } else {
+            uint64_t a, z;
+            chain_source_span(c, boff, unit_len, &lo, &z);
+            chain_source_span(c, boff + (b - 1) * stride, unit_len, &a, &hi);
+            hi = std::max(hi, z);
+        }
+        QD_TRY(stage_source(c, lo, hi, &plan));
+        const uint64_t *d_off = offsets ? static_cast<const uint64_t *>(c.offsets.p) : nullptr;
+        uint32_t *d_valid = static_cast<uint32_t *>(c.geo.p);
+
+        QD_TRY(c.prof_begin());
+        gk_geometry<<<(b + 127) / 128, 128, 0, c.stream>>>(plan, boff, stride, d_off, b, d_valid);
+        QD_LAUNCHED();
+        {
+            const uint32_t bpu = static_cast<uint32_t>((plan.n_level[0] + 255) / 256);
+            gk_source<<<b * bpu, 256, 0, c.stream>>>(plan, n_lead, boff, stride, d_off, b, d_valid,
+                                                     static_cast<float2 *>(lvl[0]->p), bpu);
+            QD_LAUNCHED();
+        }
+        for (int s = n_lead; s < S; s++) {
+            if (plan.st[s].kind == QD_STAGE_SHIFT) {
+                const uint32_t bpu = static_cast<uint32_t>((plan.n_level[s + 1] + 255) / 256);
+                gk_shift<<<b * bpu, 256, 0, c.stream>>>(plan, s, boff, stride, d_off, b, d_valid,
+                                                        static_cast<float2 *>(lvl[s + 1]->p), bpu);
+            } else {
+                const uint32_t bpu = static_cast<uint32_t>((plan.n_level[s + 1] + 127) / 128);
+                gk_lowpass<<<b * bpu, 128, 0, c.stream>>>(plan, s, b, d_valid, static_cast<const float2 *>(lvl[s]->p),
+                                                          static_cast<float2 *>(lvl[s + 1]->p), bpu);
+            }
+            QD_LAUNCHED();
+        }
+
+        const float2 *top = static_cast<const float2 *>(lvl[S]->p);
+        if (!fft_sink) QD_TRY(c.prof_end("generic: gk_source+gk_shift+gk_lowpass"));
+        if (!fft_sink) {
+            // contiguous delivery of each unit's valid samples, runs of full units in one copy
+            vcount.resize(b);
+            for (uint32_t i = 0; i < b; i++) {
+                const uint64_t o = offsets ? offsets[u0 + i] : boff + i * stride;
+                QD_TRY(chain_valid(c, o, unit_len, &vcount[i]));
+            }
+            uint32_t i = 0;
+            while (i < b) {
+                uint32_t j = i;
+                uint64_t n = 0;
+                if (vcount[i] == unit_len) {
+                    while (j < b && vcount[j] == unit_len) j++;
+                    n = static_cast<uint64_t>(j - i) * unit_len;
+                } else {
+                    n = vcount[i];
+                    j = i + 1;
+                }
+                QD_TRY(copy_out(c, sink.samples_out + produced, top + static_cast<size_t>(i) * unit_len,
+                                n * sizeof(float2), sink.space));
+                produced += n;
+                i = j;
+            }
+        } else {
+            FftArgs fa;
+            fa.in = top;
+            fa.in_pitch = unit_len;
+            fa.tw = static_cast<const float2 *>(c.twiddles.p);
+            fa.window = sink.windowed ? static_cast<const float *>(c.window.p) : nullptr;
+            fa.W = static_cast<uint32_t>(W);
+            fa.epi = sink.kind == SINK_SPARK ? EPI_SPARK : sink.kind == SINK_LEVELS ? EPI_LEVELS : EPI_TAKE;
+            fa.mn = sink.min;
+            fa.mx = sink.max;
+            fa.distinction = (sink.max - sink.min) / 7.0f; // fft.rs:45, graph.len() == 7
+            fa.idx = static_cast<uint8_t *>(c.sink_a.p);
+            fa.mag = (sink.kind == SINK_TAKE || sink.mag_out) ? static_cast<float *>(c.sink_b.p) : nullptr;
+            fa.panic_flag = d_panic;
+            const size_t smem = W * sizeof(float2) + 16;
+            if (smem > 48 * 1024)
+                QD_CUDA(cudaFuncSetAttribute(gk_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            const uint32_t threads = static_cast<uint32_t>(std::min<size_t>(256, std::max<size_t>(32, W / 4)));
+            gk_fft<<<b, threads, smem, c.stream>>>(fa);
+            QD_LAUNCHED();
+            QD_TRY(c.prof_end("generic: gk_source+gk_shift+gk_lowpass+gk_fft"));
+            if (sink.kind == SINK_SPARK) {
+                QD_TRY(copy_out(c, sink.idx_out + u0 * W, fa.idx, static_cast<size_t>(b) * W, sink.space));
+                if (sink.mag_out)
+                    QD_TRY(copy_out(c, sink.mag_out + u0 * W, fa.mag, static_cast<size_t>(b) * W * sizeof(float), sink.space));
+            } else if (sink.kind == SINK_LEVELS) {
+                QD_TRY(copy_out(c, sink.idx_out + u0, fa.idx, b, sink.space));
+            } else {
+                QD_TRY(copy_out(c, sink.mag_out + u0 * W, fa.mag, static_cast<size_t>(b) * W * sizeof(float), sink.space));
+            }
+            produced += b;
+        }
+    }
+    if (fft_sink && sink.kind == SINK_SPARK) {
+        int flag = 0;
+        QD_CUDA(cudaMemcpyAsync(&flag, d_panic, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        QD_CUDA(cudaStreamSynchronize(c.stream));
+        sink.glyph_panic = flag != 0;
+    } else if (sink.space == QD_SPACE_HOST) {
+        QD_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    if (n_out) *n_out = produced;
+    return QD_OK;
+}
+
+} // namespace qd

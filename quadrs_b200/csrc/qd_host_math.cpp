@@ -1,0 +1,105 @@
+// qd_host_math.cpp -- host-side constants of the chain: filter taps, windows, twiddles, tables.
+//
+// The reference computes these once per stage on the CPU too (LowPass::new computes its taps
+// eagerly, filter.rs:29-31).  Operation order follows the reference exactly; libm is glibc's, the
+// same one Rust's std calls.  Built with -ffp-contract=off.
+#include <cmath>
+#include <cstring>
+
+#include "qd_internal.h"
+
+namespace qd {
+
+uint64_t pair_bytes(int format)
+{ // FileFormat::pair_bytes, lib.rs:217-229
+    switch (format) {
+    case QD_FMT_CF32: return 8;
+    case QD_FMT_CS8:
+    case QD_FMT_CU8: return 2;
+    case QD_FMT_CS16: return 4;
+    default: return 0;
+    }
+}
+
+double shift_ratio(int64_t frequency, uint64_t sample_rate)
+{ // shift.rs:28 with TAU = PI * 2. (lib.rs:23)
+    const double tau = M_PI * 2.0;
+    return tau * static_cast<double>(frequency) / static_cast<double>(sample_rate);
+}
+
+void lowpass_taps(uint64_t frequency, uint64_t sample_rate, size_t size, float *out)
+{
+    // LowPass::new: cutoff_from_frequency(frequency as f64, sr) as f32  (filter.rs:29-31,126-128)
+    const float cutoff = static_cast<float>(static_cast<double>(frequency) / static_cast<double>(sample_rate));
+    const float pi = 3.14159274101257324219f; // std::f32::consts::PI
+    const float n = static_cast<float>(size);
+    for (size_t i = 0; i < size; i++) {
+        const float fi = static_cast<float>(i);
+        // blackman_window, filter.rs:91-94
+        const float w = 0.42f - 0.5f * cosf(2.0f * pi * fi / (n - 1.0f)) + 0.08f * cosf(4.0f * pi * fi / (n - 1.0f));
+        // sinc(2.0 * cutoff * (i - (size - 1)/2)), filter.rs:87-89,96-97
+        const float x = 2.0f * cutoff * (fi - (n - 1.0f) / 2.0f);
+        const float xp = x * pi;
+        out[i] = (sinf(xp) / xp) * w;
+    }
+    float sum = 0.0f; // filter.rs:103-104: sequential sum, then divide
+    for (size_t i = 0; i < size; i++) sum = sum + out[i];
+    for (size_t i = 0; i < size; i++) out[i] = out[i] / sum;
+}
+
+void blackman_harris(size_t n, float *out)
+{ // generate_blackman_harris_window, ffts.rs:110-119
+    const float tau = 6.28318530717958647692f; // std::f32::consts::TAU
+    for (size_t i = 0; i < n; i++) {
+        const float x = tau * static_cast<float>(i) / static_cast<float>(n - 1);
+        out[i] = 0.35875f - 0.48829f * cosf(x) + 0.14128f * cosf(2.0f * x) - 0.01168f * cosf(3.0f * x);
+    }
+}
+
+void fft_twiddles(size_t n, float *out)
+{
+    // Our FFT definition (rustfft 6.4.0 is not in the reference tree): w(N, j) = e^{-2 pi i j/N},
+    // angle formed in f64 as (-2 pi / N) * j, cos/sin in f64, then rounded to f32.
+    const double constant = -2.0 * M_PI / static_cast<double>(n);
+    for (size_t j = 0; j < n; j++) {
+        const double angle = constant * static_cast<double>(j);
+        out[2 * j] = static_cast<float>(cos(angle));
+        out[2 * j + 1] = static_cast<float>(sin(angle));
+    }
+}
+
+void sincos_table(double *out)
+{
+    // cos/sin(2 pi i / 256) as double-double, from 80-bit long double evaluation.
+    const long double tau = 6.283185307179586476925286766559005768L;
+    for (int i = 0; i < 256; i++) {
+        const long double a = tau * static_cast<long double>(i) / 256.0L;
+        long double c = cosl(a), s = sinl(a);
+        if (i == 0) { c = 1.0L; s = 0.0L; }
+        if (i == 64) { c = 0.0L; s = 1.0L; }
+        if (i == 128) { c = -1.0L; s = 0.0L; }
+        if (i == 192) { c = 0.0L; s = -1.0L; }
+        const double ch = static_cast<double>(c), sh = static_cast<double>(s);
+        out[4 * i + 0] = ch;
+        out[4 * i + 1] = static_cast<double>(c - static_cast<long double>(ch));
+        out[4 * i + 2] = sh;
+        out[4 * i + 3] = static_cast<double>(s - static_cast<long double>(sh));
+    }
+}
+
+void sine_table_i16(int16_t *out)
+{
+    for (int i = 0; i < 4096; i++)
+        out[i] = static_cast<int16_t>(lround(32767.0 * sin(2.0 * M_PI * static_cast<double>(i) / 4096.0)));
+}
+
+bool is_pow2(uint64_t v) { return v && !(v & (v - 1)); }
+
+uint64_t f64_as_u64(double v)
+{ // Rust `as u64`: saturating, NaN -> 0
+    if (!(v > 0.0)) return 0;
+    if (v >= 18446744073709551616.0) return UINT64_MAX;
+    return static_cast<uint64_t>(v);
+}
+
+} // namespace qd

@@ -1,0 +1,189 @@
+// qd_internal.h -- shared declarations of libquadrs_gpu (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/quadrs_gpu.h"
+
+namespace qd {
+
+// ---------------------------------------------------------------- errors
+int set_error(int code, const char *fmt, ...) __attribute__((format(printf, 2, 3)));
+const char *last_error();
+extern std::atomic<uint64_t> g_kernel_launches;
+
+#define QD_CUDA(expr)                                                                                                  \
+    do {                                                                                                               \
+        cudaError_t e_ = (expr);                                                                                       \
+        if (e_ != cudaSuccess)                                                                                         \
+            return ::qd::set_error(QD_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__,        \
+                                   __LINE__);                                                                          \
+    } while (0)
+
+#define QD_TRY(expr)                                                                                                   \
+    do {                                                                                                               \
+        int rc_ = (expr);                                                                                              \
+        if (rc_ != QD_OK) return rc_;                                                                                  \
+    } while (0)
+
+// Count a launch of one of OUR kernels and surface launch errors.
+#define QD_LAUNCHED()                                                                                                  \
+    do {                                                                                                               \
+        ::qd::g_kernel_launches.fetch_add(1, std::memory_order_relaxed);                                               \
+        QD_CUDA(cudaGetLastError());                                                                                   \
+    } while (0)
+
+// ---------------------------------------------------------------- host math (qd_host_math.cpp)
+// All of these follow the reference's f32/f64 operation order exactly; see the .cpp for file:line.
+uint64_t pair_bytes(int format);                                                   // lib.rs:217-229
+double shift_ratio(int64_t frequency, uint64_t sample_rate);                       // shift.rs:28
+void lowpass_taps(uint64_t frequency, uint64_t sample_rate, size_t size, float *out); // filter.rs:29-31,86-105
+void blackman_harris(size_t n, float *out);                                        // ffts.rs:110-119
+void fft_twiddles(size_t n, float *out_re_im);                                     // w(N,j), j<N (our FFT definition)
+void sincos_table(double *out4x256);                                               // double-double cos/sin(2 pi i/256)
+void sine_table_i16(int16_t *out4096);                                             // synthetic generator table
+bool is_pow2(uint64_t v);
+uint64_t f64_as_u64(double v);                                                     // Rust `as u64`
+
+// ---------------------------------------------------------------- chain description
+constexpr int kMaxStages = 8;
+constexpr int kMaxTones = 16;
+
+struct Stage {
+    int kind = 0; // qd_stage_kind
+    int64_t frequency = 0;
+    uint64_t decimate = 1;
+    uint64_t size = 0;    // taps
+    uint64_t rate_in = 0; // sample rate of the stage's input
+    double ratio = 0.0;   // shift
+    std::vector<float> taps;
+    float *d_taps = nullptr;
+};
+
+struct Source {
+    int kind = 0;
+    int format = 0;
+    uint64_t sample_rate = 0;
+    const uint8_t *data = nullptr; // host or device
+    uint64_t n_bytes = 0;
+    std::string path;
+    int fd = -1;
+    uint64_t base_sample = 0;
+    uint64_t resident_samples = 0; // samples available at `data`
+    uint64_t total_samples = 0;    // logical capture length
+    double gen_seconds = 0;
+    std::vector<int64_t> gen_cos;
+};
+
+// Per-device singletons (tables shared by all chains on a device).
+struct DeviceCtx {
+    int device = -1;
+    double *d_sincos = nullptr; // 256 x {cos_hi, cos_lo, sin_hi, sin_lo}
+    int16_t *d_sine_i16 = nullptr;
+    int sm_count = 0;
+};
+int device_ctx(int device, DeviceCtx **out);
+
+// Plan handed to the generic ("unit-local") kernels by value.
+struct GStage {
+    int kind;
+    uint32_t L;
+    uint64_t D;
+    double ratio;
+    const float *taps;
+};
+
+struct GPlan {
+    int n_stages;
+    int src_kind;
+    int fmt;
+    int n_tones;
+    GStage st[kMaxStages];
+    uint64_t n_level[kMaxStages + 1]; // samples requested per unit at each level (0 = source)
+    uint64_t mult[kMaxStages + 1];    // off_level = off_top * mult[level]
+    const uint8_t *src;               // device pointer to sample `src_base`
+    uint64_t src_base;
+    uint64_t src_total;
+    uint64_t src_rate;
+    int64_t tones[kMaxTones];
+    const double *sincos;
+};
+
+struct Chain {
+    Source src;
+    std::vector<Stage> stages;
+    int device = 0;
+    DeviceCtx *ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int precision = QD_PRECISION_EXACT;
+    std::mutex mu;
+
+    // device scratch (grown on demand, reused between calls)
+    struct Buf {
+        void *p = nullptr;
+        size_t cap = 0;
+    };
+    Buf stage_in;             // uploaded raw bytes for HOST_MEM / FILE sources
+    Buf level[kMaxStages + 1];
+    Buf geo;
+    Buf sink_a, sink_b, offsets;
+    Buf twiddles, window;
+    size_t twiddles_n = 0, window_n = 0;
+    void *h_pinned = nullptr; // staging for FILE sources and small D2H
+    size_t h_pinned_cap = 0;
+    size_t scratch_budget = size_t(1) << 30;
+
+    // bench instrumentation (qd_chain_profile)
+    bool profile = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    size_t prof_used = 0;
+    std::string prof_kernel;
+    int prof_begin();
+    int prof_end(const char *kernel);
+
+    ~Chain();
+    int ensure(Buf &b, size_t bytes);
+    int ensure_pinned(size_t bytes);
+};
+
+// host-side cascade (exactly the reference's len()/read_at() count arithmetic)
+int chain_len(const Chain &c, uint64_t *len);
+uint64_t chain_rate(const Chain &c);
+// samples a top-level read_at(off, n) returns; QD_E_* where the reference panics
+int chain_valid(const Chain &c, uint64_t off, uint64_t n, uint64_t *valid);
+// raw source sample range [lo, hi) a top-level read (off, n) touches (clamped to the capture)
+void chain_source_span(const Chain &c, uint64_t off, uint64_t n, uint64_t *lo, uint64_t *hi);
+
+// ---------------------------------------------------------------- executors (qd_generic.cu)
+enum SinkKind { SINK_SAMPLES = 0, SINK_SPARK = 1, SINK_LEVELS = 2, SINK_TAKE = 3 };
+
+struct SinkArgs {
+    int kind = SINK_SAMPLES;
+    size_t width = 0;
+    float min = 0.08f, max = 1.0f;
+    bool windowed = false;
+    // outputs (host or device per `space`)
+    int space = QD_SPACE_HOST;
+    qd_cf32 *samples_out = nullptr; // SINK_SAMPLES: contiguous
+    uint8_t *idx_out = nullptr;     // SINK_SPARK [units][width]; SINK_LEVELS [units]
+    float *mag_out = nullptr;       // SINK_SPARK (nullable) / SINK_TAKE [units][width]
+    bool glyph_panic = false;       // set when a bin hit the reference's graph[7] panic
+};
+
+// Runs `n_units` top-level reads of `unit_len` samples at offsets off0 + u*stride (or offsets[u])
+// through the chain and the sink.  produced[] semantics: for SINK_SAMPLES, *n_out = total samples.
+int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets, uint64_t n_units, uint64_t unit_len,
+              SinkArgs &sink, uint64_t *n_out);
+
+int synth_fill(const qd_synth *p, int format, uint64_t first, uint64_t n, void *d_out, int device, cudaStream_t st);
+
+} // namespace qd

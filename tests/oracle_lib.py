@@ -82,6 +82,8 @@ def lib():
     L.qo_last_error.restype = C.c_char_p
     L.qo_from_mem.restype = vp
     L.qo_from_mem.argtypes = [vp, u64, i32, u64]
+    L.qo_from_mem_window.restype = vp
+    L.qo_from_mem_window.argtypes = [vp, u64, i32, u64, u64, u64]
     L.qo_from_file.restype = vp
     L.qo_from_file.argtypes = [C.c_char_p, i32, u64]
     L.qo_gen.argtypes = [C.POINTER(C.c_int64), sz, u64, C.c_double, C.POINTER(vp)]
@@ -148,6 +150,14 @@ class Samples:
         h = lib().qo_from_mem(_ptr(arr), arr.size, fmt, sample_rate)
         if not h:
             raise OracleError(E_INVALID_ARG, "qo_from_mem failed")
+        return Samples(h, (arr,))
+
+    @staticmethod
+    def from_window(data: np.ndarray, fmt: int, sample_rate: int, base_sample: int, total_samples: int) -> "Samples":
+        arr = np.ascontiguousarray(data.view(np.uint8).reshape(-1))
+        h = lib().qo_from_mem_window(_ptr(arr), arr.size, fmt, sample_rate, base_sample, total_samples)
+        if not h:
+            raise OracleError(E_INVALID_ARG, "qo_from_mem_window failed")
         return Samples(h, (arr,))
 
     @staticmethod

@@ -82,3 +82,20 @@ def test_config1_fsk_structure(golden_dir):
     left = (idx[:, 24:26] > 0).any(axis=1)
     right = (idx[:, 47:49] > 0).any(axis=1)
     assert (left ^ right).mean() > 0.8
+
+
+def test_oracle_reproduces_committed_golden_vectors(golden_dir):
+    # tests/golden/*.npy were produced by tests/golden/make_golden.py with the literal convolve
+    s = O.Samples.from_file(golden_dir / "cupboard-superdec.sr400.cf32", O.CF32, 400)
+    idx, mag = s.spark_fft(4, 2, (0.001, 0.01))
+    assert np.array_equal(idx, np.load(golden_dir / "cupboard_idx.npy"))
+    assert np.array_equal(mag.view(np.uint32), np.load(golden_dir / "cupboard_mag.npy").view(np.uint32))
+    c = O.Samples.from_file(golden_dir / "fsk-example.sr21M.fc32", O.CF32, 21_000_000)
+    c = c.shift(280_000).lowpass(200_000, 32, 400)
+    O.set_kept_only(True)
+    try:
+        idx, mag = c.spark_fft(64, 16)
+    finally:
+        O.set_kept_only(False)
+    assert np.array_equal(idx, np.load(golden_dir / "config1_idx.npy"))
+    assert np.array_equal(mag.view(np.uint32), np.load(golden_dir / "config1_mag.npy").view(np.uint32))
