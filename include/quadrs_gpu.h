@@ -118,9 +118,15 @@ const char *qd_status_name(int status);
  * Performs Shift::new / LowPass::new / Gen::new checks (shift.rs:20-24, gen.rs:18-20). */
 int qd_chain_create(const qd_source *src, const qd_stage *stages, size_t n_stages, int device, qd_chain **out);
 void qd_chain_destroy(qd_chain *c);
-int qd_chain_set_stream(qd_chain *c, void *cuda_stream); /* cudaStream_t; NULL = library-owned stream */
+/* Runs the chain's kernels and copies on the caller's cudaStream_t (NULL is the legacy default
+ * stream).  A new chain owns a private non-blocking stream until this is called. */
+int qd_chain_set_stream(qd_chain *c, void *cuda_stream);
 int qd_chain_set_precision(qd_chain *c, int precision);
 int qd_chain_synchronize(qd_chain *c);
+/* Tuning knobs (tests and benches): "use_fast" 0/1 (0 forces the general unit-local executor),
+ * "segment_bytes" raw bytes staged per pipelined segment for host/file sources,
+ * "scratch_budget" bytes of device scratch the general executor may use per batch. */
+int qd_chain_set_option(qd_chain *c, const char *key, int64_t value);
 
 /* Bench instrumentation: when enabled, the kernels of every sink / read call on this chain are
  * bracketed by CUDA events on the chain's stream.  read: synchronises, then reports how many bracketed

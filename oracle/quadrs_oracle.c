@@ -982,6 +982,27 @@ int qo_write_file(qo_samples *s, const char *prefix, int overwrite, char *name_o
     QO_LEAVE(QO_OK);
 }
 
+/* Exhaustive check of the product's divide-free decode (quadrs_b200/csrc/qd_fast.cu div_exact):
+ * q0 = x*c, r = fma(-q0, den, x), q = fma(r, c, q0) with c = fl(1/den) must equal x/den for every
+ * input the formats can hold.  Returns the number of mismatches. */
+int qo_check_div_trick(void)
+{
+    const float dens[3] = {127.0f, 255.0f, 65535.0f};
+    const int los[3] = {-128, 0, -32768}, his[3] = {127, 255, 32767};
+    int bad = 0;
+    for (int k = 0; k < 3; k++) {
+        const float den = dens[k], c = 1.0f / den;
+        for (int b = los[k]; b <= his[k]; b++) {
+            const float x = (float)b;
+            const float q0 = x * c;
+            const float r = __builtin_fmaf(-q0, den, x);
+            const float q = __builtin_fmaf(r, c, q0);
+            if (q != x / den) bad++;
+        }
+    }
+    return bad;
+}
+
 /* ------------------------------------------------------------------ */
 /* timed CPU baseline                                                  */
 /* ------------------------------------------------------------------ */

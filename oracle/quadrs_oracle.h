@@ -117,6 +117,7 @@ void qo_dft_c128(const qo_cf32 *in, size_t n, double *out_re_im); /* O(n^2) comp
 double qo_shift_ratio(int64_t frequency, uint64_t sample_rate);   /* shift.rs:28 */
 /* glyph index for one magnitude (fft.rs:45,53-60); -1 where the reference panics */
 int qo_glyph_index(float norm, float min, float max);
+int qo_check_div_trick(void); /* exhaustive check of the product's divide-free decode */
 size_t qo_format_row(const uint8_t *idx, size_t width, char *out); /* fft.rs:34-36,63 */
 
 /* ---- synthetic IQ generator (CPU twin of qd_synth_fill; integer-only) ---- */

@@ -30,7 +30,7 @@ PAIR_BYTES = {FMT_CF32: 8, FMT_CS8: 2, FMT_CU8: 2, FMT_CS16: 4}
 # every symbol include/quadrs_gpu.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "qd_last_error", "qd_abi_version", "qd_device_count", "qd_kernel_launches", "qd_status_name",
-    "qd_chain_create", "qd_chain_destroy", "qd_chain_set_stream", "qd_chain_set_precision", "qd_chain_synchronize",
+    "qd_chain_create", "qd_chain_destroy", "qd_chain_set_stream", "qd_chain_set_precision", "qd_chain_synchronize", "qd_chain_set_option",
     "qd_chain_profile", "qd_chain_profile_read", "qd_chain_len", "qd_chain_sample_rate", "qd_chain_taps", "qd_chain_read_at", "qd_chain_read_exact_at",
     "qd_sparkfft_rows", "qd_sparkfft", "qd_format_row", "qd_freq_levels", "qd_take_fft", "qd_write_cf32",
     "qd_write_file", "qd_shard_plan", "qd_synth_fill",
@@ -104,6 +104,7 @@ def lib():
     L.qd_chain_set_stream.argtypes = [vp, vp]
     L.qd_chain_set_precision.argtypes = [vp, i32]
     L.qd_chain_synchronize.argtypes = [vp]
+    L.qd_chain_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.qd_chain_profile.argtypes = [vp, i32]
     L.qd_chain_profile_read.argtypes = [vp, C.POINTER(u64), C.POINTER(C.c_double), C.c_char_p, sz]
     L.qd_chain_len.argtypes = [vp, C.POINTER(u64)]

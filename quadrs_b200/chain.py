@@ -130,7 +130,7 @@ class Samples:
         self._h = h
         if self._precision != EXACT:
             L.check(lib.qd_chain_set_precision(h, self._precision))
-        if self._stream:
+        if self._stream is not None:
             L.check(lib.qd_chain_set_stream(h, self._stream))
 
     def close(self):
@@ -143,6 +143,11 @@ class Samples:
             self.close()
         except Exception:
             pass
+
+    def set_option(self, key: str, value: int) -> "Samples":
+        """Tuning knob on THIS node's chain handle ("use_fast", "segment_bytes", "scratch_budget")."""
+        L.check(L.lib().qd_chain_set_option(self._h, key.encode(), value))
+        return self
 
     def synchronize(self):
         L.check(L.lib().qd_chain_synchronize(self._h))

@@ -242,15 +242,10 @@ int qd_chain_set_stream(qd_chain *c, void *cuda_stream)
     if (!c) return set_error(QD_E_INVALID_ARG, "chain is null");
     std::lock_guard<std::mutex> lk(c->mu);
     QD_CUDA(cudaSetDevice(c->device));
-    if (c->stream) QD_CUDA(cudaStreamSynchronize(c->stream));
-    if (c->own_stream && c->stream) QD_CUDA(cudaStreamDestroy(c->stream));
-    if (cuda_stream) {
-        c->stream = static_cast<cudaStream_t>(cuda_stream);
-        c->own_stream = false;
-    } else {
-        QD_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->own_stream = true;
-    }
+    QD_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->own_stream) QD_CUDA(cudaStreamDestroy(c->stream));
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    c->own_stream = false;
     return QD_OK;
 }
 
@@ -266,6 +261,17 @@ int qd_chain_set_precision(qd_chain *c, int precision)
                          "offset formats exceeds 1e-5, so only its exact operation order reproduces it");
     std::lock_guard<std::mutex> lk(c->mu);
     c->precision = precision;
+    return QD_OK;
+}
+
+int qd_chain_set_option(qd_chain *c, const char *key, int64_t value)
+{
+    if (!c || !key) return set_error(QD_E_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!strcmp(key, "use_fast")) c->use_fast = value != 0;
+    else if (!strcmp(key, "segment_bytes") && value > 0) c->segment_bytes = static_cast<size_t>(value);
+    else if (!strcmp(key, "scratch_budget") && value > 0) c->scratch_budget = static_cast<size_t>(value);
+    else return set_error(QD_E_INVALID_ARG, "unknown option %s=%lld", key, (long long)value);
     return QD_OK;
 }
 
@@ -294,13 +300,24 @@ int qd_chain_profile_read(qd_chain *c, uint64_t *regions, double *total_ms, char
     std::lock_guard<std::mutex> lk(c->mu);
     QD_CUDA(cudaSetDevice(c->device));
     QD_CUDA(cudaStreamSynchronize(c->stream));
-    double ms = 0.0;
+    // report the kernel (region name) with the largest summed device time, and that sum
+    std::map<std::string, std::pair<double, uint64_t>> by_name;
     for (size_t i = 0; i < c->prof_used; i++) {
         float t = 0.0f;
         QD_CUDA(cudaEventElapsedTime(&t, c->prof_events[i].first, c->prof_events[i].second));
-        ms += t;
+        auto &e = by_name[c->prof_names[i]];
+        e.first += t;
+        e.second += 1;
     }
-    if (regions) *regions = c->prof_used;
+    double ms = 0.0;
+    uint64_t n = 0;
+    for (auto &kv : by_name)
+        if (kv.second.first > ms) {
+            ms = kv.second.first;
+            n = kv.second.second;
+            c->prof_kernel = kv.first;
+        }
+    if (regions) *regions = n;
     if (total_ms) *total_ms = ms;
     if (kernel_name && cap) snprintf(kernel_name, cap, "%s", c->prof_kernel.c_str());
     c->prof_used = 0;

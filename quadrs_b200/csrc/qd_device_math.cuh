@@ -71,6 +71,49 @@ __device__ __forceinline__ void sincos_f64(double theta, const double *__restric
     sd = __dadd_rn(t.z, ts);
 }
 
+// Same arithmetic with the nine f64 constants read from a kernel parameter (constant bank operands of
+// DFMA/DMUL) instead of being rebuilt in uniform registers at every use.
+struct SinCosK {
+    double K, C1, C2, s7, s5, s3, c6, c4, c2;
+};
+inline SinCosK make_sincos_k()
+{
+    SinCosK k;
+    k.K = 40.743665431525205956834243423364;
+    k.C1 = 6.283185307179586 / 256.0;
+    k.C2 = 2.4492935982947064e-16 / 256.0;
+    k.s7 = -1.0 / 5040.0;
+    k.s5 = 1.0 / 120.0;
+    k.s3 = -1.0 / 6.0;
+    k.c6 = -1.0 / 720.0;
+    k.c4 = 1.0 / 24.0;
+    k.c2 = -0.5;
+    return k;
+}
+__device__ __forceinline__ void sincos_f64k(double theta, const double *__restrict__ tab, const SinCosK &k, double &cd,
+                                            double &sd)
+{
+    const double kd = rint(__dmul_rn(theta, k.K));
+    double r = fma(-kd, k.C1, theta);
+    r = fma(-kd, k.C2, r);
+    const int ki = static_cast<int>(static_cast<long long>(kd)) & 255;
+    const double2 *tp = reinterpret_cast<const double2 *>(tab) + 2 * ki;
+    const double2 tcos = __ldg(tp), tsin = __ldg(tp + 1); // {ch, cl}, {sh, sl}
+    const double r2 = __dmul_rn(r, r);
+    double ps = fma(r2, k.s7, k.s5);
+    ps = fma(r2, ps, k.s3);
+    ps = fma(__dmul_rn(r, r2), ps, r); // sin r
+    double pc = fma(r2, k.c6, k.c4);
+    pc = fma(r2, pc, k.c2);
+    pc = __dmul_rn(r2, pc); // cos r - 1
+    double tc = fma(tcos.x, pc, tcos.y);
+    tc = fma(-tsin.x, ps, tc);
+    cd = __dadd_rn(tcos.x, tc);
+    double ts = fma(tsin.x, pc, tsin.y);
+    ts = fma(tcos.x, ps, ts);
+    sd = __dadd_rn(tsin.x, ts);
+}
+
 __device__ __forceinline__ float2 phasor_exact(uint64_t n, double ratio, const double *__restrict__ tab)
 {
     // shift.rs:49: (off + i) as f64 * self.ratio

@@ -1,0 +1,709 @@
+// qd_fast.cu -- the fused hot-path kernel: decode + NCO mix + decimating FIR in one pass.
+//
+// Canonical chain: From(cs8|cu8|cs16|cf32) -> Shift* -> LowPass, feeding do_write chunks, read_at
+// units or sparkfft windows (samples.rs:72-93 -> shift.rs:46-54 -> filter.rs:54-124).  Each raw sample
+// crosses HBM once: a persistent CTA stages a tile of raw bytes plus its (taps-1) halo in shared
+// memory with a 1-D bulk async copy (TMA, cp.async.bulk + mbarrier, double buffered), decodes and
+// mixes it once into a polyphase shared-memory layout, then computes ONLY the kept outputs, each
+// thread holding R consecutive outputs in registers so every staged sample is reused from registers.
+//
+// Arithmetic.  Per output the taps are applied in ascending order, so the reference's zero-truncated
+// tail (filter.rs:107-124: taps past the end of the caller's raw buffer contribute nothing) is simply
+// an earlier loop exit.  EXACT mode rounds the product and the sum separately (FMUL2 then FFMA2 by an
+// opaque 1.0: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2, which would change the
+// rounding) and so is bit-identical to the reference's `acc += x * f`; FAST mode uses one FFMA2.
+#include <algorithm>
+#include <cstring>
+
+#include <unistd.h>
+
+#include "qd_device_math.cuh"
+#include "qd_internal.h"
+
+namespace qd {
+
+constexpr int kFirThreads = 128;
+constexpr int kMaxTapPairs = 1024;
+constexpr int kMaxLeadShifts = 4;
+
+struct FirTaps {
+    float2 t[kMaxTapPairs]; // (f[j], f[j]) pairs, zero padded to Q*D
+};
+
+struct FirArgs {
+    const uint8_t *src; // device pointer to raw sample `src_base`
+    uint64_t src_base;
+    uint64_t src_end; // src_base + resident samples
+    int fmt;
+    int n_shift;
+    double ratio[kMaxLeadShifts];
+    const double *sincos;
+    SinCosK k;
+    uint32_t L, Q, Lrem; // L = (Q-1)*D + Lrem, 1 <= Lrem <= D
+    uint64_t off0;       // top-level (decimated) index of unit 0's first output
+    uint64_t n_call;     // outputs per unit (the n of LowPass::read_at)
+    uint64_t S;          // unit stride in top-level samples
+    uint64_t n_units;
+    int contiguous; // S == n_call: the units tile the output stream
+    uint32_t tiles_per_unit;
+    uint64_t n_tiles;
+    uint32_t raw_cap; // bytes per raw staging buffer
+    float2 *out;      // [n_units][n_call]
+    float2 one;       // (1, 1), opaque to ptxas
+};
+
+// ---------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+template <bool EXACT>
+__device__ __forceinline__ float2 mac(float2 acc, float2 x, float2 tap, float2 one)
+{
+    if (EXACT) return fma2(mul2(x, tap), one, acc); // fl(acc + fl(x*f)): filter.rs:119
+    return fma2(x, tap, acc);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+// 1-D bulk async copy global -> shared (TMA); completion is signalled on the mbarrier as bytes land
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------- exact integer decode
+// (float)v / den with the correctly rounded quotient, without the IEEE divide sequence:
+// q0 = x*c, r = fma(-q0, den, x), q = fma(r, c, q0), c = fl(1/den).  Verified exhaustively on the
+// host for every i8 / 127, u8 / 255 and i16 / 65535 (tests/test_decode_trick.py).
+__device__ __forceinline__ float div_exact(float x, float den, float c)
+{
+    const float q0 = __fmul_rn(x, c);
+    const float r = __fmaf_rn(-q0, den, x);
+    return __fmaf_rn(r, c, q0);
+}
+
+// the same, on an (I, Q) pair at once
+__device__ __forceinline__ float2 div_exact2(float2 x, float den, float c)
+{
+    const float2 c2 = make_float2(c, c);
+    const float2 q0 = mul2(x, c2);
+    const float2 r = fma2(q0, make_float2(-den, -den), x);
+    return fma2(r, c2, q0);
+}
+
+// One sample of a 4-sample group held in w[] (FMT is compile time here)
+template <int FMT>
+__device__ __forceinline__ float2 decode_in_group(const uint32_t (&w)[8], int i, float2 one)
+{
+    if (FMT == QD_FMT_CF32) return make_float2(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1])); // bit copy
+    if (FMT == QD_FMT_CS8) { // lib.rs:251
+        const uint32_t h = w[i >> 1] >> ((i & 1) * 16);
+        const float x = static_cast<float>(static_cast<int>(static_cast<signed char>(h & 0xff)));
+        const float y = static_cast<float>(static_cast<int>(static_cast<signed char>((h >> 8) & 0xff)));
+        return div_exact2(make_float2(x, y), 127.0f, 1.0f / 127.0f);
+    }
+    if (FMT == QD_FMT_CU8) { // lib.rs:252: x/255 - 127.5 (the subtraction as q*1 + (-127.5), one rounding)
+        const uint32_t h = w[i >> 1] >> ((i & 1) * 16);
+        const float x = static_cast<float>(h & 0xff), y = static_cast<float>((h >> 8) & 0xff);
+        return fma2(div_exact2(make_float2(x, y), 255.0f, 1.0f / 255.0f), one, make_float2(-127.5f, -127.5f));
+    }
+    // cs16, lib.rs:253
+    const float x = static_cast<float>(static_cast<int>(static_cast<short>(w[i] & 0xffff)));
+    const float y = static_cast<float>(static_cast<int>(static_cast<short>(w[i] >> 16)));
+    return fma2(div_exact2(make_float2(x, y), 65535.0f, 1.0f / 65535.0f), one, make_float2(-32767.5f, -32767.5f));
+}
+
+// ---------------------------------------------------------------------------- tile geometry
+constexpr int pitch_for(int G, int cols)
+{
+    // a half-warp storing 16 float2 must hit 16 distinct bank pairs: with G >= 16 consecutive lanes
+    // store to consecutive rows (odd pitch); with smaller G they alternate rows and columns
+    if (G >= 16) return cols | 1;
+    int p = cols;
+    while (p % 16 != 16 / G) p++;
+    return p;
+}
+
+template <int D, int R>
+struct FirGeom {
+    static constexpr int DR = D * R; // polyphase period
+    static constexpr int G = DR / 4; // physical rows are grouped by (row & 3)
+    static constexpr int LOG_DR = (DR == 16) ? 4 : (DR == 32) ? 5 : 6;
+    static constexpr int LOG_G = LOG_DR - 2;
+    static constexpr int T_OUT = R * kFirThreads;
+    static constexpr int COLS = kFirThreads + ((R - 1) * D + kMaxTapPairs + DR - 1) / DR + 1;
+    static constexpr int PITCH = pitch_for(G, COLS);
+    static constexpr size_t X_BYTES = static_cast<size_t>(DR) * PITCH * sizeof(float2);
+    static_assert(DR == 16 || DR == 32 || DR == 64, "polyphase period must be 16, 32 or 64");
+};
+
+struct TileGeo {
+    uint64_t n_tile0; // absolute raw index of local sample 0 (first tap of the tile's first output)
+    uint64_t out0;    // index into out[]
+    uint64_t f0;      // flat output index of the tile's first output (contiguous mode)
+    uint64_t unit;    // non-contiguous mode
+    uint32_t cnt;     // outputs in this tile
+};
+
+template <int D, int R>
+__device__ __forceinline__ TileGeo tile_geo(const FirArgs &a, uint64_t tile)
+{
+    constexpr uint32_t T_OUT = R * kFirThreads;
+    TileGeo g;
+    const uint32_t i0 = a.L - a.L / 2; // convoluted[L + k*D] is loop index L + k*D - L/2 (filter.rs:78-80,111)
+    if (a.contiguous) {
+        g.f0 = tile * T_OUT;
+        const uint64_t total = a.n_units * a.n_call;
+        g.cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(T_OUT), total - g.f0));
+        g.out0 = g.f0;
+        g.unit = 0;
+        g.n_tile0 = (a.off0 + g.f0) * D + i0;
+    } else {
+        g.unit = tile / a.tiles_per_unit;
+        const uint32_t k0 = static_cast<uint32_t>(tile % a.tiles_per_unit) * T_OUT;
+        g.cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(T_OUT), a.n_call - k0));
+        g.out0 = g.unit * a.n_call + k0;
+        g.f0 = 0;
+        g.n_tile0 = (a.off0 + g.unit * a.S + k0) * D + i0;
+    }
+    return g;
+}
+
+// ---------------------------------------------------------------------------- decode + mix stage
+// Local sample l lives at X[prow(l mod DR)][l div DR], prow(r) = (r & 3) * G + (r >> 2).  A lane
+// handles one 16-byte-aligned group of 4 raw samples; its neighbours handle the next groups, so for a
+// fixed position in the group the half-warp writes to consecutive physical rows: conflict-free.
+// ALIGNED: the tile's first sample sits on a group boundary (lead % 4 == 0), the common case, and the
+// four stores of a group are one base address plus compile-time offsets.
+__device__ __forceinline__ float2 mix_exact(float2 v, double nd, double ratio, const FirArgs &a)
+{
+    double c, sn;
+    sincos_f64k(__dmul_rn(nd, ratio), a.sincos, a.k, c, sn); // place = (off + i) as f64 * ratio, shift.rs:49
+    return cmul_exact(v, make_float2(static_cast<float>(c), static_cast<float>(sn)));
+}
+
+template <int FMT, int D, int R, bool ALIGNED>
+__device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
+                                            uint64_t n_tile0, float2 *__restrict__ X, int tid)
+{
+    using Gm = FirGeom<D, R>;
+    const int n_have = static_cast<int>(n_dec + lead);
+    const uint32_t n_groups = static_cast<uint32_t>(n_have + 3) / 4;
+    // absolute index of raw group 0, sample 0, as an exact f64 (indices stay far below 2^53)
+    const double base_d = __ull2double_rn(n_tile0 - lead);
+    const int n_shift = a.n_shift;
+    const float2 one = a.one;
+    for (uint32_t grp = tid; grp < n_groups; grp += kFirThreads) {
+        uint32_t w[8];
+        if (FMT == QD_FMT_CF32) {
+            const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp);
+            uint4 hi = make_uint4(0, 0, 0, 0);
+            if (static_cast<int>(4 * grp + 2) < n_have) hi = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp + 1);
+            w[0] = lo.x, w[1] = lo.y, w[2] = lo.z, w[3] = lo.w, w[4] = hi.x, w[5] = hi.y, w[6] = hi.z, w[7] = hi.w;
+        } else if (FMT == QD_FMT_CS16) {
+            const uint4 v = *(reinterpret_cast<const uint4 *>(raw) + grp);
+            w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
+        } else {
+            const uint2 v = *(reinterpret_cast<const uint2 *>(raw) + grp);
+            w[0] = v.x, w[1] = v.y;
+        }
+        const int g4 = static_cast<int>(4 * grp);
+        const bool interior = g4 >= static_cast<int>(lead) && g4 + 3 < n_have;
+        float2 v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = decode_in_group<FMT>(w, i, one);
+        if (n_shift) {
+            const double nd0 = __dadd_rn(base_d, static_cast<double>(g4));
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const double nd = __dadd_rn(nd0, static_cast<double>(i));
+                v[i] = mix_exact(v[i], nd, a.ratio[0], a);
+                for (int s = 1; s < n_shift; s++) v[i] = mix_exact(v[i], nd, a.ratio[s], a);
+            }
+        }
+        if (ALIGNED) {
+            const uint32_t gc = grp - (lead >> 2); // local group index (wraps for the skipped lead groups)
+            float2 *xb = X + (gc & (Gm::G - 1)) * Gm::PITCH + (gc >> Gm::LOG_G);
+            if (interior) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) xb[i * Gm::G * Gm::PITCH] = v[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    if (g4 + i >= static_cast<int>(lead) && g4 + i < n_have) xb[i * Gm::G * Gm::PITCH] = v[i];
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int l = g4 + i - static_cast<int>(lead);
+                if (l < 0 || l >= static_cast<int>(n_dec)) continue;
+                const uint32_t r = static_cast<uint32_t>(l) & (Gm::DR - 1);
+                X[((r & 3) * Gm::G + (r >> 2)) * Gm::PITCH + (static_cast<uint32_t>(l) >> Gm::LOG_DR)] = v[i];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- FIR stage
+// Block b of a thread = its local samples s = b*D .. b*D+D-1: row (b mod R)*D + p, column tid + b div R.
+template <int D, int R>
+__device__ __forceinline__ void load_block(const float2 *__restrict__ xcol, int rb, float2 (&v)[D])
+{
+    using Gm = FirGeom<D, R>;
+#pragma unroll
+    for (int p = 0; p < D; p++) {
+        const int r = rb * D + p;
+        v[p] = xcol[((r & 3) * Gm::G + (r >> 2)) * Gm::PITCH];
+    }
+}
+
+// every check at run time: prologue / epilogue blocks, partial tap blocks, truncated reads
+template <int D, int R, bool EXACT>
+__device__ __forceinline__ void general_block(const float2 *__restrict__ X, int tid, int b, int s_end, int Q, int Lrem,
+                                              const FirTaps &taps, float2 one, float2 (&acc)[R])
+{
+    const int plim = s_end - b * D;
+    if (plim <= 0) return;
+    float2 v[D];
+    load_block<D, R>(X + tid + b / R, b & (R - 1), v);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int qb = b - r; // tap block of output r at this step
+        if (qb < 0 || qb >= Q) continue;
+        const int pmax = min(plim, qb == Q - 1 ? Lrem : D);
+        const float2 *tp = taps.t + qb * D;
+#pragma unroll
+        for (int p = 0; p < D; p++)
+            if (p < pmax) acc[r] = mac<EXACT>(acc[r], v[p], tp[p], one);
+    }
+}
+
+// LS > 0: the filter length is a compile-time constant and the whole tap schedule unrolls
+template <int D, int R, bool EXACT, int LS>
+__device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid, const FirTaps &taps, float2 one,
+                                           float2 (&acc)[R])
+{
+    constexpr int Q = (LS + D - 1) / D, LREM = LS - (Q - 1) * D, NB = R - 1 + Q;
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+        float2 v[D];
+        load_block<D, R>(X + tid + b / R, b % R, v);
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int qb = b - r;
+            if (qb < 0 || qb >= Q) continue;
+#pragma unroll
+            for (int p = 0; p < D; p++)
+                if (p < (qb == Q - 1 ? LREM : D)) acc[r] = mac<EXACT>(acc[r], v[p], taps.t[qb * D + p], one);
+        }
+    }
+}
+
+template <int D, int R, bool EXACT>
+__device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int tid, int Q, int Lrem, int s_total,
+                                            const FirTaps &taps, float2 one, float2 (&acc)[R])
+{
+    const int NB = R - 1 + Q;
+    int b = 0;
+    for (; b < min(R - 1, NB); ++b) general_block<D, R, EXACT>(X, tid, b, s_total, Q, Lrem, taps, one, acc);
+    // steady state: blocks R-1 <= b < Q-1 feed every output with a full tap block
+    for (; b + R <= Q - 1; b += R) {
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            float2 v[D];
+            load_block<D, R>(X + tid + (b + k) / R, (R - 1 + k) % R, v);
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const float2 *tp = taps.t + (b + k - r) * D;
+#pragma unroll
+                for (int p = 0; p < D; p++) acc[r] = mac<EXACT>(acc[r], v[p], tp[p], one);
+            }
+        }
+    }
+    for (; b < NB; ++b) general_block<D, R, EXACT>(X, tid, b, s_total, Q, Lrem, taps, one, acc);
+}
+
+template <int D, int R, bool EXACT, int LS>
+__global__ void __launch_bounds__(kFirThreads, 2) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
+{
+    using Gm = FirGeom<D, R>;
+    constexpr int DR = Gm::DR;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
+    float2 *X = reinterpret_cast<float2 *>(smem + 16);
+    uint8_t *raw0 = smem + 16 + Gm::X_BYTES;
+    const int tid = threadIdx.x;
+    const uint32_t pb = a.fmt == QD_FMT_CF32 ? 8 : (a.fmt == QD_FMT_CS16 ? 4 : 2);
+    const bool staged = a.fmt != QD_FMT_CF32; // cf32 tiles are read straight from global memory
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // raw byte range of a tile, widened to 16-byte boundaries for the bulk copy
+    auto issue = [&](const TileGeo &g, int buf) {
+        const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + a.L;
+        const uint64_t n_dec = min(span, a.src_end - g.n_tile0);
+        const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * pb;
+        const uint8_t *abeg = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
+        const uintptr_t gend = reinterpret_cast<uintptr_t>(gbeg + n_dec * pb);
+        const uint32_t bytes = static_cast<uint32_t>(((gend + 15) & ~uintptr_t(15)) - reinterpret_cast<uintptr_t>(abeg));
+        mbar_expect_tx(&mbar[buf], bytes);
+        bulk_g2s(raw0 + static_cast<size_t>(buf) * a.raw_cap, abeg, bytes, &mbar[buf]);
+    };
+
+    uint64_t it = 0;
+    if (staged && tid == 0 && blockIdx.x < a.n_tiles) issue(tile_geo<D, R>(a, blockIdx.x), 0);
+
+    for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const int buf = static_cast<int>(it & 1);
+        const TileGeo g = tile_geo<D, R>(a, tile);
+        const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + a.L;
+        const uint32_t n_dec = static_cast<uint32_t>(min(span, a.src_end - g.n_tile0));
+        const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * pb;
+        const uint32_t lead = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gbeg) & 15) / pb;
+
+        if (staged) {
+            // prefetch the next tile's bytes while this one is decoded and filtered
+            if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, R>(a, tile + gridDim.x), buf ^ 1);
+            mbar_wait(&mbar[buf], static_cast<uint32_t>((it >> 1) & 1));
+        }
+
+        // ---- decode + mix once per sample, into the polyphase layout ------------------------------
+        {
+            const uint8_t *raw = staged ? raw0 + static_cast<size_t>(buf) * a.raw_cap
+                                        : reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
+            if ((lead & 3) == 0) {
+                switch (a.fmt) {
+                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                default: decode_tile<QD_FMT_CF32, D, R, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                }
+            } else {
+                switch (a.fmt) {
+                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                default: decode_tile<QD_FMT_CF32, D, R, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
+        if (static_cast<uint32_t>(R * tid) < g.cnt) {
+            // the unit's raw buffer ends at (unit_top0 + n_call)*D + L: later samples do not exist for
+            // this read (filter.rs:68-71) and the ascending tap loop stops there
+            uint64_t unit_top0;
+            if (a.contiguous) unit_top0 = a.off0 + ((g.f0 + static_cast<uint64_t>(R * tid)) / a.n_call) * a.n_call;
+            else unit_top0 = a.off0 + g.unit * a.S;
+            const uint64_t raw_end = (unit_top0 + a.n_call) * D + a.L;
+            const int64_t s_lim = static_cast<int64_t>(raw_end - g.n_tile0) - static_cast<int64_t>(tid) * DR;
+            const int L = LS > 0 ? LS : static_cast<int>(a.L);
+            const int s_total = (R - 1) * D + L;
+            const int Q = (L + D - 1) / D, Lrem = L - (Q - 1) * D;
+            const float2 one = a.one;
+
+            float2 acc[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f); // Complex::zero(), filter.rs:112
+
+            if (s_lim >= s_total) {
+                if (LS > 0) fir_static<D, R, EXACT, (LS > 0 ? LS : 1)>(X, tid, taps, one, acc);
+                else fir_dynamic<D, R, EXACT>(X, tid, Q, Lrem, s_total, taps, one, acc);
+            } else { // the tail of a read: outputs whose taps run past the end of the unit's raw buffer
+                const int s_end = static_cast<int>(s_lim);
+                for (int b = 0; b < R - 1 + Q; ++b) general_block<D, R, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
+            }
+            float2 *o = a.out + g.out0 + static_cast<uint64_t>(R * tid);
+            if (R % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                for (int r = 0; r < R; r += 2)
+                    *reinterpret_cast<float4 *>(o + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) o[r] = acc[r];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------- host side
+
+struct FastPlan {
+    bool ok = false;
+    int D = 0, R = 0;
+    int n_shift = 0;
+    const Stage *lp = nullptr;
+};
+
+static FastPlan fast_plan(const Chain &c, uint64_t unit_len)
+{
+    FastPlan f;
+    const Source &s = c.src;
+    if (s.kind == QD_SRC_GEN) return f;
+    const size_t S = c.stages.size();
+    if (S == 0 || c.stages[S - 1].kind != QD_STAGE_LOWPASS) return f;
+    for (size_t i = 0; i + 1 < S; i++)
+        if (c.stages[i].kind != QD_STAGE_SHIFT) return f;
+    if (S - 1 > static_cast<size_t>(kMaxLeadShifts)) return f;
+    const Stage &lp = c.stages[S - 1];
+    int R;
+    switch (lp.decimate) {
+    case 2:
+    case 4:
+    case 8: R = 8; break;
+    case 16: R = 4; break;
+    case 32: R = 2; break;
+    default: return f;
+    }
+    const uint64_t D = lp.decimate;
+    const uint64_t Q = (lp.size + D - 1) / D;
+    if (Q * D > static_cast<uint64_t>(kMaxTapPairs)) return f;
+    if (unit_len % static_cast<uint64_t>(R) != 0) return f;
+    // absolute sample 0 must sit on a 16-byte boundary so every tile's bytes can be bulk-copied
+    if (s.kind == QD_SRC_DEVICE_MEM) {
+        const uint64_t pb = pair_bytes(s.format);
+        if ((reinterpret_cast<uintptr_t>(s.data) - static_cast<uintptr_t>(s.base_sample * pb)) % 16 != 0) return f;
+    }
+    f.ok = true;
+    f.D = static_cast<int>(D);
+    f.R = R;
+    f.n_shift = static_cast<int>(S - 1);
+    f.lp = &lp;
+    return f;
+}
+
+template <int D, int R, bool EXACT, int LS>
+static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
+{
+    using Gm = FirGeom<D, R>;
+    const size_t smem = 16 + Gm::X_BYTES + 2 * static_cast<size_t>(a.raw_cap);
+    if (smem > 227 * 1024) return set_error(QD_E_INVALID_ARG, "internal: fused FIR tile needs %zu bytes of shared memory", smem);
+    const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
+    const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, 4)));
+    QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, EXACT, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    fk_fir<D, R, EXACT, LS><<<grid, kFirThreads, smem, c.stream>>>(a, t);
+    QD_LAUNCHED();
+    return QD_OK;
+}
+
+// LS = 40 is the reference's default filter (args.rs:165: `None => 40`), specialised at compile time
+template <int D, int R>
+static int launch_fir_dr(Chain &c, const FirArgs &a, const FirTaps &t, bool exact)
+{
+    if (a.L == 40) return exact ? launch_fir_k<D, R, true, 40>(c, a, t) : launch_fir_k<D, R, false, 40>(c, a, t);
+    return exact ? launch_fir_k<D, R, true, 0>(c, a, t) : launch_fir_k<D, R, false, 0>(c, a, t);
+}
+
+// Launches the fused kernel for `n_units` FULL units (no end-of-capture interaction) starting at
+// top-level offset off0 with unit stride `stride`, writing [n_units][unit_len] cf32 to d_out.
+static int launch_fir(Chain &c, const FastPlan &f, const uint8_t *d_src, uint64_t src_base, uint64_t src_end,
+                      uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_out)
+{
+    const Stage &lp = *f.lp;
+    FirArgs a;
+    memset(&a, 0, sizeof a);
+    a.src = d_src;
+    a.src_base = src_base;
+    a.src_end = src_end;
+    a.fmt = c.src.format;
+    a.n_shift = f.n_shift;
+    for (int i = 0; i < f.n_shift; i++) a.ratio[i] = c.stages[i].ratio;
+    a.sincos = c.ctx->d_sincos;
+    a.k = make_sincos_k();
+    const uint32_t D = static_cast<uint32_t>(f.D), R = static_cast<uint32_t>(f.R);
+    a.L = static_cast<uint32_t>(lp.size);
+    a.Q = (a.L + D - 1) / D;
+    a.Lrem = a.L - (a.Q - 1) * D;
+    a.off0 = off0;
+    a.n_call = unit_len;
+    a.S = stride;
+    a.n_units = n_units;
+    a.contiguous = (stride == unit_len || n_units == 1) ? 1 : 0;
+    const uint64_t t_out = static_cast<uint64_t>(R) * kFirThreads;
+    a.tiles_per_unit = static_cast<uint32_t>((unit_len + t_out - 1) / t_out);
+    a.n_tiles = a.contiguous ? (n_units * unit_len + t_out - 1) / t_out : n_units * a.tiles_per_unit;
+    const uint64_t pb = pair_bytes(a.fmt);
+    const uint64_t span_max = (t_out - 1) * D + a.L;
+    a.raw_cap = a.fmt == QD_FMT_CF32 ? 0 : static_cast<uint32_t>(((span_max * pb + 15) / 16) * 16 + 32);
+    a.out = d_out;
+    a.one = make_float2(1.0f, 1.0f);
+    FirTaps taps;
+    memset(&taps, 0, sizeof taps);
+    for (uint32_t j = 0; j < a.L; j++) taps.t[j] = make_float2(lp.taps[j], lp.taps[j]);
+
+    const bool exact = c.precision == QD_PRECISION_EXACT;
+    switch (f.D) {
+    case 2: return launch_fir_dr<2, 8>(c, a, taps, exact);
+    case 4: return launch_fir_dr<4, 8>(c, a, taps, exact);
+    case 8: return launch_fir_dr<8, 8>(c, a, taps, exact);
+    case 16: return launch_fir_dr<16, 4>(c, a, taps, exact);
+    case 32: return launch_fir_dr<32, 2>(c, a, taps, exact);
+    }
+    return set_error(QD_E_INVALID_ARG, "internal: no fused FIR for decimate %d", f.D);
+}
+
+// Number of leading units of the arithmetic progression off0 + u*stride that are FULL: the read
+// returns unit_len samples and its raw span lies inside the capture (so only the per-unit
+// truncation rule applies, never the end-of-file one).
+static uint64_t full_prefix(const Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len)
+{
+    auto full = [&](uint64_t u) {
+        uint64_t lo, hi, v = 0;
+        const uint64_t off = off0 + u * stride;
+        uint64_t n_level[kMaxStages + 1];
+        chain_source_span(c, off, unit_len, &lo, &hi);
+        (void)n_level;
+        if (chain_valid(c, off, unit_len, &v) != QD_OK || v != unit_len) return false;
+        // raw span must be un-clamped: hi - lo == unit_len*D + L
+        const Stage &lp = c.stages.back();
+        return hi - lo == unit_len * lp.decimate + lp.size;
+    };
+    if (n_units == 0) return 0;
+    if (full(n_units - 1)) return n_units;
+    if (!full(0)) return 0;
+    uint64_t lo = 0, hi = n_units - 1; // lo full, hi not
+    while (hi - lo > 1) {
+        const uint64_t mid = lo + (hi - lo) / 2;
+        if (full(mid)) lo = mid;
+        else hi = mid;
+    }
+    return lo + 1;
+}
+
+// see qd_internal.h
+int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_direct,
+                   FastSegmentFn on_segment, void *user, uint64_t *units_done)
+{
+    *units_done = 0;
+    const FastPlan f = fast_plan(c, unit_len);
+    if (!f.ok) return QD_OK;
+    const uint64_t n_full = full_prefix(c, off0, stride, n_units, unit_len);
+    if (n_full == 0) return QD_OK;
+    QD_CUDA(cudaSetDevice(c.device));
+    const Source &s = c.src;
+    const uint64_t pb = pair_bytes(s.format);
+    const Stage &lp = *f.lp;
+    const bool on_device = s.kind == QD_SRC_DEVICE_MEM;
+
+    // segment size: everything at once when both ends are resident on the device, else bounded
+    // staging buffers that are double buffered against the copies
+    uint64_t seg_units = n_full;
+    const uint64_t raw_per_unit = std::max<uint64_t>(1, std::min(stride, unit_len) * lp.decimate * pb);
+    if (!on_device) seg_units = std::max<uint64_t>(1, c.segment_bytes / raw_per_unit);
+    if (!d_direct) seg_units = std::min<uint64_t>(seg_units, std::max<uint64_t>(1, c.scratch_budget / 2 / (unit_len * sizeof(float2))));
+    seg_units = std::min(seg_units, n_full);
+
+    QD_TRY(c.ensure_pipeline());
+    // work queued earlier on the caller's stream precedes our copies
+    QD_CUDA(cudaEventRecord(c.ev_entry, c.stream));
+    QD_CUDA(cudaStreamWaitEvent(c.h2d_stream, c.ev_entry, 0));
+    QD_CUDA(cudaStreamWaitEvent(c.d2h_stream, c.ev_entry, 0));
+
+    uint64_t seg = 0;
+    for (uint64_t u0 = 0; u0 < n_full; u0 += seg_units, ++seg) {
+        const int j = static_cast<int>(seg & 1);
+        const uint64_t nu = std::min(seg_units, n_full - u0);
+        const uint64_t soff = off0 + u0 * stride;
+        uint64_t lo, hi, lo2, hi2;
+        chain_source_span(c, soff, unit_len, &lo, &hi);
+        chain_source_span(c, soff + (nu - 1) * stride, unit_len, &lo2, &hi2);
+        hi = std::max(hi, hi2);
+        if (lo < s.base_sample || hi > s.base_sample + s.resident_samples)
+            return set_error(QD_E_NOT_RESIDENT, "samples [%llu, %llu) requested but this source holds [%llu, %llu)",
+                             (unsigned long long)lo, (unsigned long long)hi, (unsigned long long)s.base_sample,
+                             (unsigned long long)(s.base_sample + s.resident_samples));
+        const uint8_t *d_src;
+        uint64_t src_base, src_end;
+        if (on_device) {
+            d_src = s.data;
+            src_base = s.base_sample;
+            src_end = s.base_sample + s.resident_samples;
+        } else {
+            // stage [lo8, hi) where lo8 keeps absolute sample 0 on a 16-byte boundary of the buffer
+            const uint64_t lo8 = lo & ~uint64_t(7);
+            const size_t bytes = static_cast<size_t>((hi - lo8) * pb);
+            QD_TRY(c.ensure(c.pipe_in[j], bytes + 64));
+            if (seg >= 2) QD_CUDA(cudaStreamWaitEvent(c.h2d_stream, c.ev_compute[j], 0)); // buffer j is free again
+            if (s.kind == QD_SRC_HOST_MEM) {
+                QD_CUDA(cudaMemcpyAsync(c.pipe_in[j].p, s.data + (lo8 - s.base_sample) * pb, bytes, cudaMemcpyHostToDevice,
+                                        c.h2d_stream));
+            } else {
+                QD_TRY(c.ensure_pinned2(j, bytes));
+                if (seg >= 2) QD_CUDA(cudaEventSynchronize(c.ev_h2d[j])); // pinned buffer j has been consumed
+                size_t done = 0;
+                while (done < bytes) {
+                    const ssize_t r = pread(s.fd, static_cast<uint8_t *>(c.h_pin2[j]) + done, bytes - done,
+                                            static_cast<off_t>(lo8 * pb + done));
+                    if (r <= 0) return set_error(QD_E_IO, "read %s: %s", s.path.c_str(), r < 0 ? strerror(errno) : "unexpected end of file");
+                    done += static_cast<size_t>(r);
+                }
+                QD_CUDA(cudaMemcpyAsync(c.pipe_in[j].p, c.h_pin2[j], bytes, cudaMemcpyHostToDevice, c.h2d_stream));
+            }
+            QD_CUDA(cudaEventRecord(c.ev_h2d[j], c.h2d_stream));
+            QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_h2d[j], 0));
+            d_src = static_cast<const uint8_t *>(c.pipe_in[j].p);
+            src_base = lo8;
+            src_end = hi;
+        }
+        float2 *d_out;
+        if (d_direct) {
+            d_out = d_direct + u0 * unit_len;
+        } else {
+            QD_TRY(c.ensure(c.pipe_out[j], nu * unit_len * sizeof(float2)));
+            if (seg >= 2) QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_d2h[j], 0)); // output staging j drained
+            d_out = static_cast<float2 *>(c.pipe_out[j].p);
+        }
+        QD_TRY(c.prof_begin());
+        QD_TRY(launch_fir(c, f, d_src, src_base, src_end, soff, stride, nu, unit_len, d_out));
+        QD_TRY(c.prof_end("fk_fir (fused decode+mix+FIR-decimate)"));
+        if (on_segment) QD_TRY(on_segment(c, user, j, u0, nu, d_out));
+        QD_CUDA(cudaEventRecord(c.ev_compute[j], c.stream));
+    }
+    *units_done = n_full;
+    return QD_OK;
+}
+
+} // namespace qd

@@ -248,6 +248,21 @@ Chain::~Chain()
     rel(offsets);
     rel(twiddles);
     rel(window);
+    rel(flag);
+    for (int j = 0; j < 2; j++) {
+        rel(pipe_in[j]);
+        rel(pipe_out[j]);
+        rel(pipe_idx[j]);
+        rel(pipe_mag[j]);
+        if (h_pin2[j]) cudaFreeHost(h_pin2[j]);
+    }
+    if (pipeline_ready) {
+        cudaStreamDestroy(h2d_stream);
+        cudaStreamDestroy(d2h_stream);
+        cudaEvent_t evs[] = {ev_entry, ev_exit, ev_h2d[0], ev_h2d[1], ev_compute[0], ev_compute[1],
+                             ev_sink[0], ev_sink[1], ev_d2h[0], ev_d2h[1]};
+        for (cudaEvent_t e : evs) cudaEventDestroy(e);
+    }
     for (auto &s : stages)
         if (s.d_taps) cudaFree(s.d_taps);
     if (h_pinned) cudaFreeHost(h_pinned);
@@ -275,8 +290,9 @@ int Chain::prof_end(const char *kernel)
 {
     if (!profile) return QD_OK;
     QD_CUDA(cudaEventRecord(prof_events[prof_used].second, stream));
+    if (prof_names.size() < prof_events.size()) prof_names.resize(prof_events.size());
+    prof_names[prof_used] = kernel;
     prof_used++;
-    prof_kernel = kernel;
     return QD_OK;
 }
 
@@ -296,6 +312,32 @@ int Chain::ensure(Buf &b, size_t bytes)
         return set_error(QD_E_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
     }
     b.cap = want;
+    return QD_OK;
+}
+
+int Chain::ensure_pipeline()
+{
+    if (pipeline_ready) return QD_OK;
+    QD_CUDA(cudaStreamCreateWithFlags(&h2d_stream, cudaStreamNonBlocking));
+    QD_CUDA(cudaStreamCreateWithFlags(&d2h_stream, cudaStreamNonBlocking));
+    cudaEvent_t *evs[] = {&ev_entry, &ev_exit, &ev_h2d[0], &ev_h2d[1], &ev_compute[0], &ev_compute[1],
+                          &ev_sink[0], &ev_sink[1], &ev_d2h[0], &ev_d2h[1]};
+    for (cudaEvent_t *e : evs) QD_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    pipeline_ready = true;
+    return QD_OK;
+}
+
+int Chain::ensure_pinned2(int j, size_t bytes)
+{
+    if (bytes <= h_pin2_cap[j]) return QD_OK;
+    if (h_pin2[j]) {
+        QD_CUDA(cudaStreamSynchronize(h2d_stream));
+        QD_CUDA(cudaFreeHost(h_pin2[j]));
+        h_pin2[j] = nullptr;
+        h_pin2_cap[j] = 0;
+    }
+    QD_CUDA(cudaMallocHost(&h_pin2[j], bytes));
+    h_pin2_cap[j] = bytes;
     return QD_OK;
 }
 
@@ -491,24 +533,91 @@ static int copy_out(Chain &c, void *dst, const void *src, size_t bytes, int spac
     return QD_OK;
 }
 
-int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets, uint64_t n_units, uint64_t unit_len,
-              SinkArgs &sink, uint64_t *n_out)
+
+static void fill_fft_args(Chain &c, const SinkArgs &sink, size_t W, FftArgs *fa)
 {
-    if (n_out) *n_out = 0;
-    if (n_units == 0 || unit_len == 0) return QD_OK;
-    QD_CUDA(cudaSetDevice(c.device));
+    fa->in_pitch = W;
+    fa->tw = static_cast<const float2 *>(c.twiddles.p);
+    fa->window = sink.windowed ? static_cast<const float *>(c.window.p) : nullptr;
+    fa->W = static_cast<uint32_t>(W);
+    fa->epi = sink.kind == SINK_SPARK ? EPI_SPARK : sink.kind == SINK_LEVELS ? EPI_LEVELS : EPI_TAKE;
+    fa->mn = sink.min;
+    fa->mx = sink.max;
+    fa->distinction = (sink.max - sink.min) / 7.0f; // fft.rs:45, graph.len() == 7
+    fa->panic_flag = static_cast<int *>(c.flag.p);
+}
+
+static int launch_fft(Chain &c, const FftArgs &fa, uint32_t units)
+{
+    const size_t smem = fa.W * sizeof(float2) + 16;
+    if (smem > 48 * 1024)
+        QD_CUDA(cudaFuncSetAttribute(gk_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const uint32_t threads = static_cast<uint32_t>(std::min<size_t>(256, std::max<size_t>(32, fa.W / 4)));
+    gk_fft<<<units, threads, smem, c.stream>>>(fa);
+    QD_LAUNCHED();
+    return QD_OK;
+}
+
+// element sizes of the sink's per-unit outputs
+static size_t sink_idx_bytes(const SinkArgs &s, size_t W) { return s.kind == SINK_LEVELS ? 1 : (s.kind == SINK_SPARK ? W : 0); }
+static bool sink_has_mag(const SinkArgs &s) { return s.kind == SINK_TAKE || (s.kind == SINK_SPARK && s.mag_out); }
+
+// Sink processing of one fused-path segment: d_top holds [nu][unit_len] cf32 for units u0.. of the call.
+struct FastSinkCtx {
+    SinkArgs *sink;
+    uint64_t unit_len;
+};
+
+static int fast_segment_sink(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, const float2 *d_top)
+{
+    FastSinkCtx *ctx = static_cast<FastSinkCtx *>(user);
+    SinkArgs &sink = *ctx->sink;
+    const size_t W = sink.width;
+    const bool to_host = sink.space == QD_SPACE_HOST;
+    if (sink.kind == SINK_SAMPLES) {
+        if (!to_host) return QD_OK; // the kernel wrote straight into the caller's device buffer
+        QD_CUDA(cudaEventRecord(c.ev_sink[j], c.stream));
+        QD_CUDA(cudaStreamWaitEvent(c.d2h_stream, c.ev_sink[j], 0));
+        QD_CUDA(cudaMemcpyAsync(sink.samples_out + u0 * ctx->unit_len, d_top, nu * ctx->unit_len * sizeof(float2),
+                                cudaMemcpyDeviceToHost, c.d2h_stream));
+        QD_CUDA(cudaEventRecord(c.ev_d2h[j], c.d2h_stream));
+        return QD_OK;
+    }
+    FftArgs fa;
+    fill_fft_args(c, sink, W, &fa);
+    fa.in = d_top;
+    const size_t ib = sink_idx_bytes(sink, W);
+    const bool mag = sink_has_mag(sink);
+    if (to_host) {
+        if (ib) QD_TRY(c.ensure(c.pipe_idx[j], nu * ib));
+        if (mag) QD_TRY(c.ensure(c.pipe_mag[j], nu * W * sizeof(float)));
+        fa.idx = static_cast<uint8_t *>(c.pipe_idx[j].p);
+        fa.mag = mag ? static_cast<float *>(c.pipe_mag[j].p) : nullptr;
+    } else {
+        fa.idx = ib ? sink.idx_out + u0 * ib : nullptr;
+        fa.mag = mag ? sink.mag_out + u0 * W : nullptr;
+    }
+    QD_TRY(launch_fft(c, fa, static_cast<uint32_t>(nu)));
+    if (to_host) {
+        QD_CUDA(cudaEventRecord(c.ev_sink[j], c.stream));
+        QD_CUDA(cudaStreamWaitEvent(c.d2h_stream, c.ev_sink[j], 0));
+        if (ib) QD_CUDA(cudaMemcpyAsync(sink.idx_out + u0 * ib, fa.idx, nu * ib, cudaMemcpyDeviceToHost, c.d2h_stream));
+        if (mag)
+            QD_CUDA(cudaMemcpyAsync(sink.mag_out + u0 * W, fa.mag, nu * W * sizeof(float), cudaMemcpyDeviceToHost, c.d2h_stream));
+        QD_CUDA(cudaEventRecord(c.ev_d2h[j], c.d2h_stream));
+    }
+    return QD_OK;
+}
+
+// The unit-local path for units [u_begin, n_units) of the call.
+static int run_units_generic(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets, uint64_t u_begin,
+                             uint64_t n_units, uint64_t unit_len, SinkArgs &sink, uint64_t *produced_io)
+{
     GPlan plan;
     QD_TRY(fill_plan(c, unit_len, &plan));
     const int S = plan.n_stages;
     const size_t W = sink.width;
     const bool fft_sink = sink.kind != SINK_SAMPLES;
-    if (fft_sink) {
-        if (W != unit_len) return set_error(QD_E_INVALID_ARG, "internal: fft sink width != unit length");
-        if (W * sizeof(float2) + 16 > 200 * 1024)
-            return set_error(QD_E_INVALID_ARG, "fft width %zu exceeds the supported maximum of 16384", W);
-        QD_TRY(ensure_twiddles(c, W));
-        if (sink.windowed) QD_TRY(ensure_window(c, W));
-    }
 
     // leading shifts ride along with the source kernel
     int n_lead = 0;
@@ -520,7 +629,7 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
         if (l == 0 || plan.st[l - 1].kind == QD_STAGE_LOWPASS) per_unit += plan.n_level[l] * sizeof(float2);
     if (fft_sink) per_unit += W * (sizeof(uint8_t) + sizeof(float));
     uint64_t B = std::max<uint64_t>(1, c.scratch_budget / std::max<size_t>(per_unit, 1));
-    B = std::min<uint64_t>(B, std::min<uint64_t>(n_units, 32768));
+    B = std::min<uint64_t>(B, std::min<uint64_t>(n_units - u_begin, 32768));
 
     Chain::Buf *lvl[kMaxStages + 1];
     for (int l = 0; l <= S; l++) {
@@ -531,18 +640,19 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
             lvl[l] = lvl[l - 1];
         }
     }
-    QD_TRY(c.ensure(c.geo, B * (S + 1) * sizeof(uint32_t) + sizeof(int)));
-    int *d_panic = reinterpret_cast<int *>(static_cast<uint8_t *>(c.geo.p) + B * (S + 1) * sizeof(uint32_t));
-    if (fft_sink) {
-        QD_TRY(c.ensure(c.sink_a, B * (sink.kind == SINK_LEVELS ? 1 : W)));
-        if (sink.kind == SINK_TAKE || sink.mag_out) QD_TRY(c.ensure(c.sink_b, B * W * sizeof(float)));
-        QD_CUDA(cudaMemsetAsync(d_panic, 0, sizeof(int), c.stream));
+    QD_TRY(c.ensure(c.geo, B * (S + 1) * sizeof(uint32_t)));
+    const size_t ib = sink_idx_bytes(sink, W);
+    const bool mag = sink_has_mag(sink);
+    const bool to_host = sink.space == QD_SPACE_HOST;
+    if (fft_sink && to_host) {
+        if (ib) QD_TRY(c.ensure(c.sink_a, B * ib));
+        if (mag) QD_TRY(c.ensure(c.sink_b, B * W * sizeof(float)));
     }
     if (offsets) QD_TRY(c.ensure(c.offsets, B * sizeof(uint64_t)));
 
-    uint64_t produced = 0;
+    uint64_t produced = *produced_io;
     std::vector<uint64_t> vcount;
-    for (uint64_t u0 = 0; u0 < n_units; u0 += B) {
+    for (uint64_t u0 = u_begin; u0 < n_units; u0 += B) {
         const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(B, n_units - u0));
         const uint64_t boff = off0 + u0 * stride;
 
@@ -590,8 +700,8 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
         }
 
         const float2 *top = static_cast<const float2 *>(lvl[S]->p);
-        if (!fft_sink) QD_TRY(c.prof_end("generic: gk_source+gk_shift+gk_lowpass"));
         if (!fft_sink) {
+            QD_TRY(c.prof_end("generic: gk_source+gk_shift+gk_lowpass"));
             // contiguous delivery of each unit's valid samples, runs of full units in one copy
             vcount.resize(b);
             for (uint32_t i = 0; i < b; i++) {
@@ -616,40 +726,67 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
             }
         } else {
             FftArgs fa;
+            fill_fft_args(c, sink, W, &fa);
             fa.in = top;
-            fa.in_pitch = unit_len;
-            fa.tw = static_cast<const float2 *>(c.twiddles.p);
-            fa.window = sink.windowed ? static_cast<const float *>(c.window.p) : nullptr;
-            fa.W = static_cast<uint32_t>(W);
-            fa.epi = sink.kind == SINK_SPARK ? EPI_SPARK : sink.kind == SINK_LEVELS ? EPI_LEVELS : EPI_TAKE;
-            fa.mn = sink.min;
-            fa.mx = sink.max;
-            fa.distinction = (sink.max - sink.min) / 7.0f; // fft.rs:45, graph.len() == 7
-            fa.idx = static_cast<uint8_t *>(c.sink_a.p);
-            fa.mag = (sink.kind == SINK_TAKE || sink.mag_out) ? static_cast<float *>(c.sink_b.p) : nullptr;
-            fa.panic_flag = d_panic;
-            const size_t smem = W * sizeof(float2) + 16;
-            if (smem > 48 * 1024)
-                QD_CUDA(cudaFuncSetAttribute(gk_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            const uint32_t threads = static_cast<uint32_t>(std::min<size_t>(256, std::max<size_t>(32, W / 4)));
-            gk_fft<<<b, threads, smem, c.stream>>>(fa);
-            QD_LAUNCHED();
-            QD_TRY(c.prof_end("generic: gk_source+gk_shift+gk_lowpass+gk_fft"));
-            if (sink.kind == SINK_SPARK) {
-                QD_TRY(copy_out(c, sink.idx_out + u0 * W, fa.idx, static_cast<size_t>(b) * W, sink.space));
-                if (sink.mag_out)
-                    QD_TRY(copy_out(c, sink.mag_out + u0 * W, fa.mag, static_cast<size_t>(b) * W * sizeof(float), sink.space));
-            } else if (sink.kind == SINK_LEVELS) {
-                QD_TRY(copy_out(c, sink.idx_out + u0, fa.idx, b, sink.space));
+            if (to_host) {
+                fa.idx = static_cast<uint8_t *>(c.sink_a.p);
+                fa.mag = mag ? static_cast<float *>(c.sink_b.p) : nullptr;
             } else {
-                QD_TRY(copy_out(c, sink.mag_out + u0 * W, fa.mag, static_cast<size_t>(b) * W * sizeof(float), sink.space));
+                fa.idx = ib ? sink.idx_out + u0 * ib : nullptr;
+                fa.mag = mag ? sink.mag_out + u0 * W : nullptr;
+            }
+            QD_TRY(launch_fft(c, fa, b));
+            QD_TRY(c.prof_end("generic: gk_source+gk_shift+gk_lowpass+gk_fft"));
+            if (to_host) {
+                if (ib) QD_TRY(copy_out(c, sink.idx_out + u0 * ib, fa.idx, static_cast<size_t>(b) * ib, sink.space));
+                if (mag) QD_TRY(copy_out(c, sink.mag_out + u0 * W, fa.mag, static_cast<size_t>(b) * W * sizeof(float), sink.space));
             }
             produced += b;
         }
     }
+    *produced_io = produced;
+    return QD_OK;
+}
+
+int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets, uint64_t n_units, uint64_t unit_len,
+              SinkArgs &sink, uint64_t *n_out)
+{
+    if (n_out) *n_out = 0;
+    if (n_units == 0 || unit_len == 0) return QD_OK;
+    QD_CUDA(cudaSetDevice(c.device));
+    const size_t W = sink.width;
+    const bool fft_sink = sink.kind != SINK_SAMPLES;
+    if (fft_sink) {
+        if (W != unit_len) return set_error(QD_E_INVALID_ARG, "internal: fft sink width != unit length");
+        if (W * sizeof(float2) + 16 > 200 * 1024)
+            return set_error(QD_E_INVALID_ARG, "fft width %zu exceeds the supported maximum of 16384", W);
+        QD_TRY(ensure_twiddles(c, W));
+        if (sink.windowed) QD_TRY(ensure_window(c, W));
+        QD_TRY(c.ensure(c.flag, sizeof(int)));
+        QD_CUDA(cudaMemsetAsync(c.flag.p, 0, sizeof(int), c.stream));
+    }
+
+    uint64_t produced = 0, done = 0;
+    bool used_pipeline = false;
+    if (!offsets && c.use_fast) {
+        FastSinkCtx ctx{&sink, unit_len};
+        float2 *direct = (sink.kind == SINK_SAMPLES && sink.space == QD_SPACE_DEVICE)
+                             ? reinterpret_cast<float2 *>(sink.samples_out)
+                             : nullptr;
+        QD_TRY(run_units_fast(c, off0, stride, n_units, unit_len, direct, fast_segment_sink, &ctx, &done));
+        used_pipeline = done > 0;
+        produced = sink.kind == SINK_SAMPLES ? done * unit_len : done;
+        if (used_pipeline) {
+            // later work on the caller's stream (and the generic remainder) follows the drain copies
+            QD_CUDA(cudaEventRecord(c.ev_exit, c.d2h_stream));
+            QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_exit, 0));
+        }
+    }
+    if (done < n_units) QD_TRY(run_units_generic(c, off0, stride, offsets, done, n_units, unit_len, sink, &produced));
+
     if (fft_sink && sink.kind == SINK_SPARK) {
         int flag = 0;
-        QD_CUDA(cudaMemcpyAsync(&flag, d_panic, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+        QD_CUDA(cudaMemcpyAsync(&flag, c.flag.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
         QD_CUDA(cudaStreamSynchronize(c.stream));
         sink.glyph_panic = flag != 0;
     } else if (sink.space == QD_SPACE_HOST) {

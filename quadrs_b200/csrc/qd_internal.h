@@ -141,12 +141,28 @@ struct Chain {
     void *h_pinned = nullptr; // staging for FILE sources and small D2H
     size_t h_pinned_cap = 0;
     size_t scratch_budget = size_t(1) << 30;
+    Buf flag; // glyph-panic flag of the spark sink
+
+    // fused path (qd_fast.cu): segments are double buffered against H2D and D2H copies
+    bool use_fast = true;
+    size_t segment_bytes = size_t(64) << 20; // raw bytes staged per segment for host / file sources
+    bool pipeline_ready = false;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_entry = nullptr, ev_exit = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_sink[2] = {nullptr, nullptr},
+                ev_d2h[2] = {nullptr, nullptr};
+    Buf pipe_in[2], pipe_out[2], pipe_idx[2], pipe_mag[2];
+    void *h_pin2[2] = {nullptr, nullptr};
+    size_t h_pin2_cap[2] = {0, 0};
+    int ensure_pipeline();
+    int ensure_pinned2(int j, size_t bytes);
 
     // bench instrumentation (qd_chain_profile)
     bool profile = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
     size_t prof_used = 0;
     std::string prof_kernel;
+    std::vector<std::string> prof_names;
     int prof_begin();
     int prof_end(const char *kernel);
 
@@ -183,6 +199,15 @@ struct SinkArgs {
 // through the chain and the sink.  produced[] semantics: for SINK_SAMPLES, *n_out = total samples.
 int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets, uint64_t n_units, uint64_t unit_len,
               SinkArgs &sink, uint64_t *n_out);
+
+// Fused path (qd_fast.cu).  Handles the leading run of FULL units of the progression off0 + u*stride
+// when the chain is From -> Shift* -> LowPass with a supported decimation; *units_done = how many.
+// Output of segment units [u0, u0+nu) is [nu][unit_len] cf32 at d_direct + u0*unit_len when d_direct
+// is given, else in a library staging buffer; on_segment (nullable) is called after each segment's
+// kernel has been enqueued on c.stream, with j = staging slot.
+typedef int (*FastSegmentFn)(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, const float2 *d_top);
+int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_direct,
+                   FastSegmentFn on_segment, void *user, uint64_t *units_done);
 
 int synth_fill(const qd_synth *p, int format, uint64_t first, uint64_t n, void *d_out, int device, cudaStream_t st);
 

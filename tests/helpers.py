@@ -33,7 +33,13 @@ def gpu_chain(raw, fmt, rate, stages, base=0, total=0, precision=None):
 
 
 def bits(a: np.ndarray) -> np.ndarray:
-    return np.ascontiguousarray(a).view(np.uint32)
+    """f32 words with every NaN canonicalised: x86 and sm_100 generate different default NaN patterns
+    (0xFFC00000 vs 0x7FFFFFFF) for the same invalid operation (e.g. the 0/0 centre tap of an odd-length
+    filter, filter.rs:87-89); NaN payloads copied from the input are compared by test_decode_bit_exact."""
+    w = np.ascontiguousarray(a).view(np.uint32).copy()
+    f = w.view(np.float32)
+    w[np.isnan(f)] = 0x7FC00000
+    return w
 
 
 def assert_bit_equal(got, want, what=""):

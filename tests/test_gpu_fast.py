@@ -1,0 +1,210 @@
+"""The fused kernel (qd_fast.cu) against the oracle and against the general unit-local executor, the
+pipelined host path, sharding, and size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from helpers import assert_bit_equal, gpu_chain, kept_only, oracle_chain, synth_raw
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Q():
+    import quadrs_b200
+
+    return quadrs_b200
+
+
+CASES = [
+    # fmt, stages, sink
+    (O.CS8, [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)], ("write", 0x1000)),          # config 2
+    (O.CS8, [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)], ("spark", 64, 16, (0.05, 2.0))),
+    (O.CU8, [("lowpass", 1_000_000, 8, 40)], ("write", 0x1000)),
+    (O.CS16, [("shift", 7_000_000), ("lowpass", 2_000_000, 16, 800)], ("spark", 128, 128, (0.5, 50.0))),  # config 4
+    (O.CF32, [("shift", 280_000), ("lowpass", 200_000, 32, 400)], ("spark", 64, 16, None)),       # config 1
+    (O.CF32, [("lowpass", 3_000_000, 4, 22)], ("write", 0x1000)),
+    (O.CS16, [("shift", -1_000_000), ("shift", 2_500_000), ("lowpass", 2_000_000, 2, 9 * 2)], ("write", 512)),
+    (O.CS8, [("lowpass", 1_000_000, 8, 37)], ("write", 64)),  # odd filter length: NaN taps, still the same order
+    (O.CS8, [("shift", 3_000_000), ("lowpass", 500_000, 16, 100)], ("spark", 32, 7, (0.01, 1.0))),
+    (O.CU8, [("shift", 3_000_000), ("lowpass", 500_000, 32, 40)], ("spark", 4, 2, (0.01, 1.0))),
+]
+
+
+def _run(chain, sink):
+    if sink[0] == "write":
+        data, rc = chain.write_mem(chunk=sink[1])
+        return data, rc
+    idx, mag = chain.spark_fft(sink[1], sink[2], sink[3], want_mag=True)
+    return (idx, mag), 0
+
+
+@pytest.mark.parametrize("fmt,stages,sink", CASES)
+def test_fused_matches_oracle_and_general_executor(Q, fmt, stages, sink):
+    n = 150_000
+    raw, _ = synth_raw(fmt, n, rate=100e6)
+    fused = gpu_chain(raw, fmt, 100_000_000, stages)
+    general = gpu_chain(raw, fmt, 100_000_000, stages).set_option("use_fast", 0)
+    launches0 = Q._lib.lib().qd_kernel_launches()
+    got, rc = _run(fused, sink)
+    assert Q._lib.lib().qd_kernel_launches() > launches0
+    ref, rc2 = _run(general, sink)
+    with kept_only():
+        want, rc3 = _run_oracle(oracle_chain(raw, fmt, 100_000_000, stages), sink)
+    assert rc == rc2 == rc3
+    if sink[0] == "write":
+        assert_bit_equal(got, ref, "fused vs general executor")
+        assert_bit_equal(got, want, "fused vs oracle")
+    else:
+        assert np.array_equal(got[0], ref[0]) and np.array_equal(got[0], want[0])
+        assert_bit_equal(got[1], ref[1], "magnitudes fused vs general")
+        assert_bit_equal(got[1], want[1], "magnitudes fused vs oracle")
+
+
+def _run_oracle(chain, sink):
+    if sink[0] == "write":
+        return chain.write_mem(chunk=sink[1])
+    idx, mag = chain.spark_fft(sink[1], sink[2], sink[3])
+    return (idx, mag), 0
+
+
+@pytest.mark.parametrize("seg", [40_000, 1_000_000])
+def test_pipelined_host_and_file_sources(Q, tmp_path, seg):
+    n = 700_000
+    raw, _ = synth_raw(O.CS8, n)
+    st = [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)]
+    with kept_only():
+        want, want_rc = oracle_chain(raw, O.CS8, 20_000_000, st).write_mem()
+        widx, _ = oracle_chain(raw, O.CS8, 20_000_000, st).spark_fft(64, 64, (0.05, 2.0))
+    host = gpu_chain(raw, O.CS8, 20_000_000, st).set_option("segment_bytes", seg)
+    got, rc = host.write_mem()
+    assert rc == want_rc
+    assert_bit_equal(got, want, "pipelined host source")
+    idx, _ = host.spark_fft(64, 64, (0.05, 2.0))
+    assert np.array_equal(idx, widx)
+    path = tmp_path / "cap.sr20M.cs8"
+    raw.tofile(path)
+    f = Q.Samples.from_file(path, Q.CS8, 20_000_000).shift(1_500_000).lowpass(1_000_000, 8, 40)
+    f.set_option("segment_bytes", seg)
+    got, rc = f.write_mem()
+    assert rc == want_rc
+    assert_bit_equal(got, want, "pipelined file source")
+
+
+def test_sharded_equals_unsharded(Q):
+    # contiguous unit ranges, halo of (taps, window) samples, absolute indices: no hand-off
+    n = 1_000_000
+    raw, _ = synth_raw(O.CS16, n, rate=100e6)
+    st = [("shift", 7_000_000), ("lowpass", 2_000_000, 16, 800)]
+    whole = gpu_chain(raw, O.CS16, 100_000_000, st)
+    idx, _ = whole.spark_fft(128, 128, (0.5, 50.0))
+    data, _ = whole.write_mem()
+    for n_shards in (2, 3):
+        rows, outs = [], []
+        for r in range(n_shards):
+            p = Q.shard_plan(Q.CS16, 100_000_000, n, st, Q.shard.SINK_SPARKFFT, 128, 128, n_shards, r)
+            part = raw[p.first_sample * 4 : (p.first_sample + p.n_samples) * 4]
+            g = gpu_chain(part, O.CS16, 100_000_000, st, base=p.first_sample, total=n)
+            got, _ = g.spark_fft(128, 128, (0.5, 50.0), first_row=p.first_unit, max_rows=p.n_units)
+            rows.append(got)
+            w = Q.shard_plan(Q.CS16, 100_000_000, n, st, Q.shard.SINK_WRITE, 0x1000, 0x1000, n_shards, r)
+            part = raw[w.first_sample * 4 : (w.first_sample + w.n_samples) * 4]
+            g = gpu_chain(part, O.CS16, 100_000_000, st, base=w.first_sample, total=n)
+            o, _ = g.write_mem(first_chunk=w.first_unit, max_chunks=w.n_units)
+            outs.append(o)
+        assert np.array_equal(np.concatenate(rows), idx)
+        assert_bit_equal(np.concatenate(outs), data, f"{n_shards} shards")
+
+
+def _oracle_rows_from_device(Q, torch, d_in, fmt, rate, total, base, stages, W, S, rng, rows, need):
+    """Oracle rows computed from the device input's own bytes around each sampled row."""
+    out = []
+    pb = O.FORMAT_BYTES[fmt]
+    mult = 1
+    for st in stages:
+        if st[0] == "lowpass":
+            mult *= st[2]
+    for r in rows:
+        lo = r * S * mult
+        hi = min(lo + need, total)
+        raw = d_in[(lo - base) * pb : (hi - base) * pb].cpu().numpy()
+        with kept_only():
+            idx, mag = oracle_chain(raw, fmt, rate, stages, lo, total).spark_fft(W, S, rng, first_row=r, max_rows=1)
+        out.append((idx[0], mag[0]))
+    return out
+
+
+def test_full_size_config2_checks(Q):
+    """BASELINE.json configs[1] at full size (2^30 cs8 samples): sampled chunks against the oracle, and
+    the whole 1 GiB output against a two-shard run (equality of every byte = a checksum of checksums)."""
+    import torch
+
+    n = 2**30
+    fmt, rate = Q.CS8, 20_000_000
+    st = [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)]
+    synth = Q.make_synth(0x5EED0002, [(Q.tone_step(1.6e6, rate), 45, 0), (Q.tone_step(-4.1e6, rate), 30, 0),
+                                      (Q.tone_step(0.3e6, rate), 20, 3000)], 6)
+    d_in = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    Q.synth_fill_device(synth, fmt, 0, n, d_in.data_ptr())
+    torch.cuda.synchronize()
+    chain = Q.Samples.from_device(d_in.data_ptr(), 2 * n, fmt, rate, keep=(d_in,)).shift(1_500_000).lowpass(1_000_000, 8, 40)
+    ln = chain.len()
+    assert ln == 1 + (n - 40) // 8
+    chunks = -(-ln // 0x1000)
+    d_out = torch.zeros(2 * chunks * 0x1000, dtype=torch.float32, device="cuda")
+    # one read more than there are chunks: the reference's loop makes it too, gets 0 samples and panics
+    got_n, rc = chain.write_into(0x1000, 0, chunks + 1, d_out.data_ptr(), chunks * 0x1000, Q._lib.SPACE_DEVICE)
+    chain.synchronize()
+    assert rc == Q._lib.E_WRITE_SHORT and got_n == ln - 1  # lib.rs:203 fires after the last readable sample
+    # sampled chunks vs the oracle (first, interior at 2^k boundaries, last full, ragged tail)
+    for c in (0, 1, 12_345, chunks // 2, chunks - 3, chunks - 2, chunks - 1):
+        lo = c * 0x1000 * 8
+        hi = min(lo + 0x1000 * 8 + 40, n)
+        raw = d_in[2 * lo : 2 * hi].cpu().numpy()
+        with kept_only():
+            want, _ = oracle_chain(raw, O.CS8, rate, st, lo, n).write_mem(first_chunk=c, max_chunks=1)
+        got = d_out[2 * c * 0x1000 : 2 * (c * 0x1000 + len(want))].cpu().numpy().view(np.complex64)
+        assert_bit_equal(got, want, f"chunk {c}")
+    # two shards reproduce every output sample of the unsharded run
+    d_out2 = torch.zeros_like(d_out)
+    for r in range(2):
+        p = Q.shard_plan(fmt, rate, n, st, Q.shard.SINK_WRITE, 0x1000, 0x1000, 2, r)
+        view = d_in[2 * p.first_sample : 2 * (p.first_sample + p.n_samples)]
+        g = Q.Samples.from_device(view.data_ptr(), view.numel(), fmt, rate, base_sample=p.first_sample, total_samples=n,
+                                  keep=(d_in,)).shift(1_500_000).lowpass(1_000_000, 8, 40)
+        off = 2 * p.first_unit * 0x1000
+        g.write_into(0x1000, p.first_unit, p.n_units, d_out2.data_ptr() + 4 * off, p.n_units * 0x1000, Q._lib.SPACE_DEVICE)
+        g.synchronize()
+    assert torch.equal(d_out, d_out2)
+    out_head = d_out[: 2 * 65536].cpu().numpy()
+    assert np.isfinite(out_head).all() and np.abs(out_head).max() > 0
+
+
+def test_full_size_config4_shape_sampled_rows(Q):
+    """BASELINE.json configs[3] shape on a 2^28-sample shard of the 2^33 capture, at its absolute place."""
+    import torch
+
+    total, n = 2**33, 2**28
+    base = total - n
+    fmt, rate = Q.CS16, 100_000_000
+    st = [("shift", 7_000_000), ("lowpass", 2_000_000, 16, 800)]
+    synth = Q.make_synth(0x5EED0004, [(Q.tone_step(7.3e6, rate), 9000, 0), (Q.tone_step(6.2e6, rate), 6000, 50_000),
+                                      (Q.tone_step(-20e6, rate), 4000, 0)], 1200)
+    d_in = torch.empty(4 * n, dtype=torch.uint8, device="cuda")
+    Q.synth_fill_device(synth, fmt, base, n, d_in.data_ptr())
+    torch.cuda.synchronize()
+    chain = Q.Samples.from_device(d_in.data_ptr(), 4 * n, fmt, rate, base_sample=base, total_samples=total, keep=(d_in,))
+    chain = chain.shift(7_000_000).lowpass(2_000_000, 16, 800)
+    rows_total = chain.spark_rows(128, 128)
+    assert rows_total == 4_194_303
+    first = -(-base // (128 * 16))
+    n_rows = rows_total - first
+    d_idx = torch.zeros(n_rows * 128, dtype=torch.uint8, device="cuda")
+    assert chain.spark_fft_device(128, 128, (0.5, 50.0), first, n_rows, d_idx.data_ptr()) == n_rows
+    chain.synchronize()
+    idx = d_idx.cpu().numpy().reshape(n_rows, 128)
+    assert idx.max() <= 8
+    rows = [first, first + 1, first + 77_777, rows_total - 2, rows_total - 1]
+    want = _oracle_rows_from_device(Q, torch, d_in, O.CS16, rate, total, base, st, 128, 128, (0.5, 50.0), rows, 128 * 16 + 800)
+    for r, (widx, _) in zip(rows, want):
+        assert np.array_equal(idx[r - first], widx), f"row {r}"
