@@ -22,7 +22,6 @@
 
 namespace qd {
 
-constexpr int kFirThreads = 128;
 constexpr int kMaxTapPairs = 1024;
 constexpr int kMaxLeadShifts = 4;
 
@@ -160,14 +159,14 @@ constexpr int pitch_for(int G, int cols)
     return p;
 }
 
-template <int D, int R>
+template <int D, int R, int NT>
 struct FirGeom {
     static constexpr int DR = D * R; // polyphase period
     static constexpr int G = DR / 4; // physical rows are grouped by (row & 3)
     static constexpr int LOG_DR = (DR == 16) ? 4 : (DR == 32) ? 5 : 6;
     static constexpr int LOG_G = LOG_DR - 2;
-    static constexpr int T_OUT = R * kFirThreads;
-    static constexpr int COLS = kFirThreads + ((R - 1) * D + kMaxTapPairs + DR - 1) / DR + 1;
+    static constexpr int T_OUT = R * NT;
+    static constexpr int COLS = NT + ((R - 1) * D + kMaxTapPairs + DR - 1) / DR + 1;
     static constexpr int PITCH = pitch_for(G, COLS);
     static constexpr size_t X_BYTES = static_cast<size_t>(DR) * PITCH * sizeof(float2);
     static_assert(DR == 16 || DR == 32 || DR == 64, "polyphase period must be 16, 32 or 64");
@@ -181,10 +180,9 @@ struct TileGeo {
     uint32_t cnt;     // outputs in this tile
 };
 
-template <int D, int R>
+template <int D, int T_OUT>
 __device__ __forceinline__ TileGeo tile_geo(const FirArgs &a, uint64_t tile)
 {
-    constexpr uint32_t T_OUT = R * kFirThreads;
     TileGeo g;
     const uint32_t i0 = a.L - a.L / 2; // convoluted[L + k*D] is loop index L + k*D - L/2 (filter.rs:78-80,111)
     if (a.contiguous) {
@@ -218,18 +216,18 @@ __device__ __forceinline__ float2 mix_exact(float2 v, double nd, double ratio, c
     return cmul_exact(v, make_float2(static_cast<float>(c), static_cast<float>(sn)));
 }
 
-template <int FMT, int D, int R, bool ALIGNED>
+template <int FMT, int D, int R, int NT, bool ALIGNED>
 __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
                                             uint64_t n_tile0, float2 *__restrict__ X, int tid)
 {
-    using Gm = FirGeom<D, R>;
+    using Gm = FirGeom<D, R, NT>;
     const int n_have = static_cast<int>(n_dec + lead);
     const uint32_t n_groups = static_cast<uint32_t>(n_have + 3) / 4;
     // absolute index of raw group 0, sample 0, as an exact f64 (indices stay far below 2^53)
     const double base_d = __ull2double_rn(n_tile0 - lead);
     const int n_shift = a.n_shift;
     const float2 one = a.one;
-    for (uint32_t grp = tid; grp < n_groups; grp += kFirThreads) {
+    for (uint32_t grp = tid; grp < n_groups; grp += NT) {
         uint32_t w[8];
         if (FMT == QD_FMT_CF32) {
             const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp);
@@ -282,10 +280,10 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
 
 // ---------------------------------------------------------------------------- FIR stage
 // Block b of a thread = its local samples s = b*D .. b*D+D-1: row (b mod R)*D + p, column tid + b div R.
-template <int D, int R>
+template <int D, int R, int NT>
 __device__ __forceinline__ void load_block(const float2 *__restrict__ xcol, int rb, float2 (&v)[D])
 {
-    using Gm = FirGeom<D, R>;
+    using Gm = FirGeom<D, R, NT>;
 #pragma unroll
     for (int p = 0; p < D; p++) {
         const int r = rb * D + p;
@@ -294,14 +292,14 @@ __device__ __forceinline__ void load_block(const float2 *__restrict__ xcol, int 
 }
 
 // every check at run time: prologue / epilogue blocks, partial tap blocks, truncated reads
-template <int D, int R, bool EXACT>
+template <int D, int R, int NT, bool EXACT>
 __device__ __forceinline__ void general_block(const float2 *__restrict__ X, int tid, int b, int s_end, int Q, int Lrem,
                                               const FirTaps &taps, float2 one, float2 (&acc)[R])
 {
     const int plim = s_end - b * D;
     if (plim <= 0) return;
     float2 v[D];
-    load_block<D, R>(X + tid + b / R, b & (R - 1), v);
+    load_block<D, R, NT>(X + tid + b / R, b & (R - 1), v);
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int qb = b - r; // tap block of output r at this step
@@ -315,7 +313,7 @@ __device__ __forceinline__ void general_block(const float2 *__restrict__ X, int 
 }
 
 // LS > 0: the filter length is a compile-time constant and the whole tap schedule unrolls
-template <int D, int R, bool EXACT, int LS>
+template <int D, int R, int NT, bool EXACT, int LS>
 __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid, const FirTaps &taps, float2 one,
                                            float2 (&acc)[R])
 {
@@ -323,7 +321,7 @@ __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         float2 v[D];
-        load_block<D, R>(X + tid + b / R, b % R, v);
+        load_block<D, R, NT>(X + tid + b / R, b % R, v);
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int qb = b - r;
@@ -335,19 +333,19 @@ __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid
     }
 }
 
-template <int D, int R, bool EXACT>
+template <int D, int R, int NT, bool EXACT>
 __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int tid, int Q, int Lrem, int s_total,
                                             const FirTaps &taps, float2 one, float2 (&acc)[R])
 {
     const int NB = R - 1 + Q;
     int b = 0;
-    for (; b < min(R - 1, NB); ++b) general_block<D, R, EXACT>(X, tid, b, s_total, Q, Lrem, taps, one, acc);
+    for (; b < min(R - 1, NB); ++b) general_block<D, R, NT, EXACT>(X, tid, b, s_total, Q, Lrem, taps, one, acc);
     // steady state: blocks R-1 <= b < Q-1 feed every output with a full tap block
     for (; b + R <= Q - 1; b += R) {
 #pragma unroll
         for (int k = 0; k < R; k++) {
             float2 v[D];
-            load_block<D, R>(X + tid + (b + k) / R, (R - 1 + k) % R, v);
+            load_block<D, R, NT>(X + tid + (b + k) / R, (R - 1 + k) % R, v);
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const float2 *tp = taps.t + (b + k - r) * D;
@@ -356,13 +354,13 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
             }
         }
     }
-    for (; b < NB; ++b) general_block<D, R, EXACT>(X, tid, b, s_total, Q, Lrem, taps, one, acc);
+    for (; b < NB; ++b) general_block<D, R, NT, EXACT>(X, tid, b, s_total, Q, Lrem, taps, one, acc);
 }
 
-template <int D, int R, bool EXACT, int LS>
-__global__ void __launch_bounds__(kFirThreads, 2) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
+template <int D, int R, int NT, bool EXACT, int LS>
+__global__ void __launch_bounds__(NT, 2) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
 {
-    using Gm = FirGeom<D, R>;
+    using Gm = FirGeom<D, R, NT>;
     constexpr int DR = Gm::DR;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
@@ -392,11 +390,11 @@ __global__ void __launch_bounds__(kFirThreads, 2) fk_fir(const __grid_constant__
     };
 
     uint64_t it = 0;
-    if (staged && tid == 0 && blockIdx.x < a.n_tiles) issue(tile_geo<D, R>(a, blockIdx.x), 0);
+    if (staged && tid == 0 && blockIdx.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, blockIdx.x), 0);
 
     for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const int buf = static_cast<int>(it & 1);
-        const TileGeo g = tile_geo<D, R>(a, tile);
+        const TileGeo g = tile_geo<D, Gm::T_OUT>(a, tile);
         const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + a.L;
         const uint32_t n_dec = static_cast<uint32_t>(min(span, a.src_end - g.n_tile0));
         const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * pb;
@@ -404,7 +402,7 @@ __global__ void __launch_bounds__(kFirThreads, 2) fk_fir(const __grid_constant__
 
         if (staged) {
             // prefetch the next tile's bytes while this one is decoded and filtered
-            if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, R>(a, tile + gridDim.x), buf ^ 1);
+            if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x), buf ^ 1);
             mbar_wait(&mbar[buf], static_cast<uint32_t>((it >> 1) & 1));
         }
 
@@ -414,17 +412,17 @@ __global__ void __launch_bounds__(kFirThreads, 2) fk_fir(const __grid_constant__
                                         : reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
             if ((lead & 3) == 0) {
                 switch (a.fmt) {
-                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                default: decode_tile<QD_FMT_CF32, D, R, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                default: decode_tile<QD_FMT_CF32, D, R, NT, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
                 }
             } else {
                 switch (a.fmt) {
-                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                default: decode_tile<QD_FMT_CF32, D, R, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                default: decode_tile<QD_FMT_CF32, D, R, NT, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
                 }
             }
         }
@@ -449,11 +447,11 @@ __global__ void __launch_bounds__(kFirThreads, 2) fk_fir(const __grid_constant__
             for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f); // Complex::zero(), filter.rs:112
 
             if (s_lim >= s_total) {
-                if (LS > 0) fir_static<D, R, EXACT, (LS > 0 ? LS : 1)>(X, tid, taps, one, acc);
-                else fir_dynamic<D, R, EXACT>(X, tid, Q, Lrem, s_total, taps, one, acc);
+                if (LS > 0) fir_static<D, R, NT, EXACT, (LS > 0 ? LS : 1)>(X, tid, taps, one, acc);
+                else fir_dynamic<D, R, NT, EXACT>(X, tid, Q, Lrem, s_total, taps, one, acc);
             } else { // the tail of a read: outputs whose taps run past the end of the unit's raw buffer
                 const int s_end = static_cast<int>(s_lim);
-                for (int b = 0; b < R - 1 + Q; ++b) general_block<D, R, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
+                for (int b = 0; b < R - 1 + Q; ++b) general_block<D, R, NT, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
             }
             float2 *o = a.out + g.out0 + static_cast<uint64_t>(R * tid);
             if (R % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
@@ -471,9 +469,25 @@ __global__ void __launch_bounds__(kFirThreads, 2) fk_fir(const __grid_constant__
 
 // ---------------------------------------------------------------------------- host side
 
+// (decimate) -> outputs per thread R and threads per CTA; R * NT * D ~ 8192 raw samples per tile
+struct FirShape {
+    int R, NT;
+};
+static bool fir_shape(uint64_t D, FirShape *s)
+{
+    switch (D) {
+    case 2: *s = {8, 128}; return true;
+    case 4: *s = {8, 128}; return true;
+    case 8: *s = {4, 256}; return true;
+    case 16: *s = {4, 128}; return true;
+    case 32: *s = {2, 128}; return true;
+    }
+    return false;
+}
+
 struct FastPlan {
     bool ok = false;
-    int D = 0, R = 0;
+    int D = 0, R = 0, NT = 0;
     int n_shift = 0;
     const Stage *lp = nullptr;
 };
@@ -489,15 +503,9 @@ static FastPlan fast_plan(const Chain &c, uint64_t unit_len)
         if (c.stages[i].kind != QD_STAGE_SHIFT) return f;
     if (S - 1 > static_cast<size_t>(kMaxLeadShifts)) return f;
     const Stage &lp = c.stages[S - 1];
-    int R;
-    switch (lp.decimate) {
-    case 2:
-    case 4:
-    case 8: R = 8; break;
-    case 16: R = 4; break;
-    case 32: R = 2; break;
-    default: return f;
-    }
+    FirShape shape;
+    if (!fir_shape(lp.decimate, &shape)) return f;
+    const int R = shape.R;
     const uint64_t D = lp.decimate;
     const uint64_t Q = (lp.size + D - 1) / D;
     if (Q * D > static_cast<uint64_t>(kMaxTapPairs)) return f;
@@ -510,32 +518,35 @@ static FastPlan fast_plan(const Chain &c, uint64_t unit_len)
     f.ok = true;
     f.D = static_cast<int>(D);
     f.R = R;
+    f.NT = shape.NT;
     f.n_shift = static_cast<int>(S - 1);
     f.lp = &lp;
     return f;
 }
 
-template <int D, int R, bool EXACT, int LS>
+template <int D, int R, int NT, bool EXACT, int LS>
 static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
 {
-    using Gm = FirGeom<D, R>;
+    using Gm = FirGeom<D, R, NT>;
     const size_t smem = 16 + Gm::X_BYTES + 2 * static_cast<size_t>(a.raw_cap);
     if (smem > 227 * 1024) return set_error(QD_E_INVALID_ARG, "internal: fused FIR tile needs %zu bytes of shared memory", smem);
     const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
     const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, 4)));
-    QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, EXACT, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    fk_fir<D, R, EXACT, LS><<<grid, kFirThreads, smem, c.stream>>>(a, t);
+    QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    fk_fir<D, R, NT, EXACT, LS><<<grid, NT, smem, c.stream>>>(a, t);
     QD_LAUNCHED();
     return QD_OK;
 }
 
 // LS = 40 is the reference's default filter (args.rs:165: `None => 40`), specialised at compile time
-template <int D, int R>
+template <int D, int R, int NT>
 static int launch_fir_dr(Chain &c, const FirArgs &a, const FirTaps &t, bool exact)
 {
-    if (a.L == 40) return exact ? launch_fir_k<D, R, true, 40>(c, a, t) : launch_fir_k<D, R, false, 40>(c, a, t);
-    return exact ? launch_fir_k<D, R, true, 0>(c, a, t) : launch_fir_k<D, R, false, 0>(c, a, t);
+    if (a.L == 40) return exact ? launch_fir_k<D, R, NT, true, 40>(c, a, t) : launch_fir_k<D, R, NT, false, 40>(c, a, t);
+    return exact ? launch_fir_k<D, R, NT, true, 0>(c, a, t) : launch_fir_k<D, R, NT, false, 0>(c, a, t);
 }
+
+
 
 // Launches the fused kernel for `n_units` FULL units (no end-of-capture interaction) starting at
 // top-level offset off0 with unit stride `stride`, writing [n_units][unit_len] cf32 to d_out.
@@ -562,7 +573,7 @@ static int launch_fir(Chain &c, const FastPlan &f, const uint8_t *d_src, uint64_
     a.S = stride;
     a.n_units = n_units;
     a.contiguous = (stride == unit_len || n_units == 1) ? 1 : 0;
-    const uint64_t t_out = static_cast<uint64_t>(R) * kFirThreads;
+    const uint64_t t_out = static_cast<uint64_t>(R) * f.NT;
     a.tiles_per_unit = static_cast<uint32_t>((unit_len + t_out - 1) / t_out);
     a.n_tiles = a.contiguous ? (n_units * unit_len + t_out - 1) / t_out : n_units * a.tiles_per_unit;
     const uint64_t pb = pair_bytes(a.fmt);
@@ -576,11 +587,11 @@ static int launch_fir(Chain &c, const FastPlan &f, const uint8_t *d_src, uint64_
 
     const bool exact = c.precision == QD_PRECISION_EXACT;
     switch (f.D) {
-    case 2: return launch_fir_dr<2, 8>(c, a, taps, exact);
-    case 4: return launch_fir_dr<4, 8>(c, a, taps, exact);
-    case 8: return launch_fir_dr<8, 8>(c, a, taps, exact);
-    case 16: return launch_fir_dr<16, 4>(c, a, taps, exact);
-    case 32: return launch_fir_dr<32, 2>(c, a, taps, exact);
+    case 2: return launch_fir_dr<2, 8, 128>(c, a, taps, exact);
+    case 4: return launch_fir_dr<4, 8, 128>(c, a, taps, exact);
+    case 8: return launch_fir_dr<8, 4, 256>(c, a, taps, exact);
+    case 16: return launch_fir_dr<16, 4, 128>(c, a, taps, exact);
+    case 32: return launch_fir_dr<32, 2, 128>(c, a, taps, exact);
     }
     return set_error(QD_E_INVALID_ARG, "internal: no fused FIR for decimate %d", f.D);
 }
