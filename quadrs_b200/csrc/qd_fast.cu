@@ -46,6 +46,7 @@ struct FirArgs {
     int contiguous; // S == n_call: the units tile the output stream
     uint32_t tiles_per_unit;
     uint64_t n_tiles;
+    uint64_t total_out; // contiguous mode: outputs to compute (<= n_units * n_call)
     uint32_t raw_cap; // bytes per raw staging buffer
     float2 *out;      // [n_units][n_call]
     float2 one;       // (1, 1), opaque to ptxas
@@ -187,7 +188,7 @@ __device__ __forceinline__ TileGeo tile_geo(const FirArgs &a, uint64_t tile)
     const uint32_t i0 = a.L - a.L / 2; // convoluted[L + k*D] is loop index L + k*D - L/2 (filter.rs:78-80,111)
     if (a.contiguous) {
         g.f0 = tile * T_OUT;
-        const uint64_t total = a.n_units * a.n_call;
+        const uint64_t total = a.total_out;
         g.cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(T_OUT), total - g.f0));
         g.out0 = g.f0;
         g.unit = 0;
@@ -485,45 +486,6 @@ static bool fir_shape(uint64_t D, FirShape *s)
     return false;
 }
 
-struct FastPlan {
-    bool ok = false;
-    int D = 0, R = 0, NT = 0;
-    int n_shift = 0;
-    const Stage *lp = nullptr;
-};
-
-static FastPlan fast_plan(const Chain &c, uint64_t unit_len)
-{
-    FastPlan f;
-    const Source &s = c.src;
-    if (s.kind == QD_SRC_GEN) return f;
-    const size_t S = c.stages.size();
-    if (S == 0 || c.stages[S - 1].kind != QD_STAGE_LOWPASS) return f;
-    for (size_t i = 0; i + 1 < S; i++)
-        if (c.stages[i].kind != QD_STAGE_SHIFT) return f;
-    if (S - 1 > static_cast<size_t>(kMaxLeadShifts)) return f;
-    const Stage &lp = c.stages[S - 1];
-    FirShape shape;
-    if (!fir_shape(lp.decimate, &shape)) return f;
-    const int R = shape.R;
-    const uint64_t D = lp.decimate;
-    const uint64_t Q = (lp.size + D - 1) / D;
-    if (Q * D > static_cast<uint64_t>(kMaxTapPairs)) return f;
-    if (unit_len % static_cast<uint64_t>(R) != 0) return f;
-    // absolute sample 0 must sit on a 16-byte boundary so every tile's bytes can be bulk-copied
-    if (s.kind == QD_SRC_DEVICE_MEM) {
-        const uint64_t pb = pair_bytes(s.format);
-        if ((reinterpret_cast<uintptr_t>(s.data) - static_cast<uintptr_t>(s.base_sample * pb)) % 16 != 0) return f;
-    }
-    f.ok = true;
-    f.D = static_cast<int>(D);
-    f.R = R;
-    f.NT = shape.NT;
-    f.n_shift = static_cast<int>(S - 1);
-    f.lp = &lp;
-    return f;
-}
-
 template <int D, int R, int NT, bool EXACT, int LS>
 static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
 {
@@ -546,54 +508,119 @@ static int launch_fir_dr(Chain &c, const FirArgs &a, const FirTaps &t, bool exac
     return exact ? launch_fir_k<D, R, NT, true, 0>(c, a, t) : launch_fir_k<D, R, NT, false, 0>(c, a, t);
 }
 
+// One LowPass stage as the fused kernel sees it
+struct LpInfo {
+    const Stage *st = nullptr;
+    uint32_t D = 0, L = 0, i0 = 0;
+    uint32_t T = 0; // outputs at the end of every read that use a truncated filter: (n-k)*D + L/2 < L
+    FirShape shape{0, 0};
+};
 
+struct FastPlan {
+    bool ok = false;
+    int n_shift = 0;
+    int n_lp = 0;
+    LpInfo lp[2];
+    // The top stage's outputs do not depend on the read they belong to (no truncated positions), so it is
+    // materialised once as a contiguous stream and windows are taken from it at the sink's stride.
+    bool stream_top = false;
+};
 
-// Launches the fused kernel for `n_units` FULL units (no end-of-capture interaction) starting at
-// top-level offset off0 with unit stride `stride`, writing [n_units][unit_len] cf32 to d_out.
-static int launch_fir(Chain &c, const FastPlan &f, const uint8_t *d_src, uint64_t src_base, uint64_t src_end,
-                      uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_out)
+static bool lp_info(const Stage &st, LpInfo *o)
 {
-    const Stage &lp = *f.lp;
+    if (st.kind != QD_STAGE_LOWPASS || !fir_shape(st.decimate, &o->shape)) return false;
+    o->st = &st;
+    o->D = static_cast<uint32_t>(st.decimate);
+    o->L = static_cast<uint32_t>(st.size);
+    const uint64_t Q = (st.size + o->D - 1) / o->D;
+    if (Q * o->D > static_cast<uint64_t>(kMaxTapPairs)) return false;
+    o->i0 = o->L - o->L / 2;
+    o->T = (o->i0 + o->D - 1) / o->D - 1;
+    return true;
+}
+
+static FastPlan fast_plan(const Chain &c, uint64_t unit_len, uint64_t stride, uint64_t n_units)
+{
+    FastPlan f;
+    const Source &s = c.src;
+    if (s.kind == QD_SRC_GEN) return f;
+    const size_t S = c.stages.size();
+    size_t i = 0;
+    while (i < S && c.stages[i].kind == QD_STAGE_SHIFT) i++;
+    if (i > static_cast<size_t>(kMaxLeadShifts)) return f;
+    f.n_shift = static_cast<int>(i);
+    f.n_lp = static_cast<int>(S - i);
+    if (f.n_lp < 1 || f.n_lp > 2) return f;
+    for (int k = 0; k < f.n_lp; k++)
+        if (!lp_info(c.stages[i + k], &f.lp[k])) return f;
+    const LpInfo &top = f.lp[f.n_lp - 1];
+    if (f.n_lp == 2) {
+        // The inner stage can only be shared between units if no unit ever reads the truncated tail of
+        // its own inner read: the outer stage must be free of truncation (T == 0, i.e. D2 >= i0_2) and its
+        // last tap must stop T1 samples short of the inner buffer's end (D2 - i0_2 >= T1).
+        if (top.T != 0 || top.D - top.i0 < f.lp[0].T) return f;
+        f.stream_top = true;
+    } else {
+        f.stream_top = top.T == 0 && stride != unit_len && n_units > 1;
+    }
+    if (!f.stream_top && unit_len % static_cast<uint64_t>(top.shape.R) != 0) return f;
+    // absolute sample 0 must sit on a 16-byte boundary so every tile's bytes can be bulk-copied
+    if (s.kind == QD_SRC_DEVICE_MEM) {
+        const uint64_t pb = pair_bytes(s.format);
+        if ((reinterpret_cast<uintptr_t>(s.data) - static_cast<uintptr_t>(s.base_sample * pb)) % 16 != 0) return f;
+    }
+    f.ok = true;
+    return f;
+}
+
+// One fused-kernel launch.  The source is raw capture bytes (fmt, shifts) or a cf32 stream from an earlier
+// stage.  n_units units of n_call outputs at unit stride S (top-level samples) starting at off0, written as
+// [n_units][n_call]; total_out limits the count in contiguous mode.
+static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const double *ratios, const uint8_t *d_src,
+                      uint64_t src_base, uint64_t src_end, uint64_t off0, uint64_t n_call, uint64_t S, uint64_t n_units,
+                      uint64_t total_out, float2 *d_out)
+{
+    const Stage &st = *lp.st;
     FirArgs a;
     memset(&a, 0, sizeof a);
     a.src = d_src;
     a.src_base = src_base;
     a.src_end = src_end;
-    a.fmt = c.src.format;
-    a.n_shift = f.n_shift;
-    for (int i = 0; i < f.n_shift; i++) a.ratio[i] = c.stages[i].ratio;
+    a.fmt = fmt;
+    a.n_shift = n_shift;
+    for (int i = 0; i < n_shift; i++) a.ratio[i] = ratios[i];
     a.sincos = c.ctx->d_sincos;
     a.k = make_sincos_k();
-    const uint32_t D = static_cast<uint32_t>(f.D), R = static_cast<uint32_t>(f.R);
-    a.L = static_cast<uint32_t>(lp.size);
+    const uint32_t D = lp.D, R = static_cast<uint32_t>(lp.shape.R);
+    a.L = lp.L;
     a.Q = (a.L + D - 1) / D;
     a.Lrem = a.L - (a.Q - 1) * D;
     a.off0 = off0;
-    a.n_call = unit_len;
-    a.S = stride;
+    a.n_call = n_call;
+    a.S = S;
     a.n_units = n_units;
-    a.contiguous = (stride == unit_len || n_units == 1) ? 1 : 0;
-    const uint64_t t_out = static_cast<uint64_t>(R) * f.NT;
-    a.tiles_per_unit = static_cast<uint32_t>((unit_len + t_out - 1) / t_out);
-    a.n_tiles = a.contiguous ? (n_units * unit_len + t_out - 1) / t_out : n_units * a.tiles_per_unit;
-    const uint64_t pb = pair_bytes(a.fmt);
+    a.contiguous = (S == n_call || n_units == 1) ? 1 : 0;
+    a.total_out = total_out;
+    const uint64_t t_out = static_cast<uint64_t>(R) * lp.shape.NT;
+    a.tiles_per_unit = static_cast<uint32_t>((n_call + t_out - 1) / t_out);
+    a.n_tiles = a.contiguous ? (total_out + t_out - 1) / t_out : n_units * a.tiles_per_unit;
+    const uint64_t pb = pair_bytes(fmt);
     const uint64_t span_max = (t_out - 1) * D + a.L;
-    a.raw_cap = a.fmt == QD_FMT_CF32 ? 0 : static_cast<uint32_t>(((span_max * pb + 15) / 16) * 16 + 32);
+    a.raw_cap = fmt == QD_FMT_CF32 ? 0 : static_cast<uint32_t>(((span_max * pb + 15) / 16) * 16 + 32);
     a.out = d_out;
     a.one = make_float2(1.0f, 1.0f);
     FirTaps taps;
     memset(&taps, 0, sizeof taps);
-    for (uint32_t j = 0; j < a.L; j++) taps.t[j] = make_float2(lp.taps[j], lp.taps[j]);
-
+    for (uint32_t j = 0; j < a.L; j++) taps.t[j] = make_float2(st.taps[j], st.taps[j]);
     const bool exact = c.precision == QD_PRECISION_EXACT;
-    switch (f.D) {
+    switch (D) {
     case 2: return launch_fir_dr<2, 8, 128>(c, a, taps, exact);
     case 4: return launch_fir_dr<4, 8, 128>(c, a, taps, exact);
     case 8: return launch_fir_dr<8, 4, 256>(c, a, taps, exact);
     case 16: return launch_fir_dr<16, 4, 128>(c, a, taps, exact);
     case 32: return launch_fir_dr<32, 2, 128>(c, a, taps, exact);
     }
-    return set_error(QD_E_INVALID_ARG, "internal: no fused FIR for decimate %d", f.D);
+    return set_error(QD_E_INVALID_ARG, "internal: no fused FIR for decimate %u", D);
 }
 
 // Number of leading units of the arithmetic progression off0 + u*stride that are FULL: the read
@@ -601,16 +628,15 @@ static int launch_fir(Chain &c, const FastPlan &f, const uint8_t *d_src, uint64_
 // truncation rule applies, never the end-of-file one).
 static uint64_t full_prefix(const Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len)
 {
+    uint64_t need = unit_len; // raw samples an un-clamped read touches
+    for (size_t s = c.stages.size(); s-- > 0;)
+        if (c.stages[s].kind == QD_STAGE_LOWPASS) need = need * c.stages[s].decimate + c.stages[s].size;
     auto full = [&](uint64_t u) {
         uint64_t lo, hi, v = 0;
         const uint64_t off = off0 + u * stride;
-        uint64_t n_level[kMaxStages + 1];
         chain_source_span(c, off, unit_len, &lo, &hi);
-        (void)n_level;
         if (chain_valid(c, off, unit_len, &v) != QD_OK || v != unit_len) return false;
-        // raw span must be un-clamped: hi - lo == unit_len*D + L
-        const Stage &lp = c.stages.back();
-        return hi - lo == unit_len * lp.decimate + lp.size;
+        return hi - lo == need;
     };
     if (n_units == 0) return 0;
     if (full(n_units - 1)) return n_units;
@@ -624,27 +650,40 @@ static uint64_t full_prefix(const Chain &c, uint64_t off0, uint64_t stride, uint
     return lo + 1;
 }
 
+static uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
+
+constexpr uint64_t kStreamCall = uint64_t(1) << 40; // "one read that never ends": no truncation inside a stream
+
 // see qd_internal.h
-int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_direct,
-                   FastSegmentFn on_segment, void *user, uint64_t *units_done)
+int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, bool samples_sink,
+                   float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done)
 {
     *units_done = 0;
-    const FastPlan f = fast_plan(c, unit_len);
+    const FastPlan f = fast_plan(c, unit_len, stride, n_units);
     if (!f.ok) return QD_OK;
     const uint64_t n_full = full_prefix(c, off0, stride, n_units, unit_len);
     if (n_full == 0) return QD_OK;
     QD_CUDA(cudaSetDevice(c.device));
     const Source &s = c.src;
     const uint64_t pb = pair_bytes(s.format);
-    const Stage &lp = *f.lp;
     const bool on_device = s.kind == QD_SRC_DEVICE_MEM;
+    const LpInfo &top = f.lp[f.n_lp - 1];
+    uint64_t mult = 1; // raw samples per top-level sample
+    for (int k = 0; k < f.n_lp; k++) mult *= f.lp[k].D;
+    if (f.stream_top) d_direct = nullptr; // streams are padded: never written into the caller's buffer
+    double ratios[kMaxLeadShifts];
+    for (int i = 0; i < f.n_shift; i++) ratios[i] = c.stages[i].ratio;
 
     // segment size: everything at once when both ends are resident on the device, else bounded
     // staging buffers that are double buffered against the copies
     uint64_t seg_units = n_full;
-    const uint64_t raw_per_unit = std::max<uint64_t>(1, std::min(stride, unit_len) * lp.decimate * pb);
+    const uint64_t raw_per_unit = std::max<uint64_t>(1, std::min(stride, unit_len) * mult * pb);
     if (!on_device) seg_units = std::max<uint64_t>(1, c.segment_bytes / raw_per_unit);
-    if (!d_direct) seg_units = std::min<uint64_t>(seg_units, std::max<uint64_t>(1, c.scratch_budget / 2 / (unit_len * sizeof(float2))));
+    if (!d_direct) {
+        const uint64_t per_unit_out = (f.stream_top ? std::min(stride, unit_len) : unit_len) * sizeof(float2) *
+                                      (f.n_lp == 2 ? (1 + top.D) : 1);
+        seg_units = std::min<uint64_t>(seg_units, std::max<uint64_t>(1, c.scratch_budget / 2 / std::max<uint64_t>(1, per_unit_out)));
+    }
     seg_units = std::min(seg_units, n_full);
 
     QD_TRY(c.ensure_pipeline());
@@ -699,20 +738,54 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
             src_base = lo8;
             src_end = hi;
         }
-        float2 *d_out;
-        if (d_direct) {
-            d_out = d_direct + u0 * unit_len;
-        } else {
-            QD_TRY(c.ensure(c.pipe_out[j], nu * unit_len * sizeof(float2)));
-            if (seg >= 2) QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_d2h[j], 0)); // output staging j drained
-            d_out = static_cast<float2 *>(c.pipe_out[j].p);
-        }
+        if (seg >= 2) QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_d2h[j], 0)); // output staging j drained
+
+        const float2 *d_top;
+        uint64_t pitch;
         QD_TRY(c.prof_begin());
-        QD_TRY(launch_fir(c, f, d_src, src_base, src_end, soff, stride, nu, unit_len, d_out));
+        if (!f.stream_top) {
+            // [nu][unit_len] matrix straight from the raw bytes, per-unit truncation applied in the kernel
+            float2 *d_out;
+            if (d_direct) {
+                d_out = d_direct + u0 * unit_len;
+            } else {
+                QD_TRY(c.ensure(c.pipe_out[j], nu * unit_len * sizeof(float2)));
+                d_out = static_cast<float2 *>(c.pipe_out[j].p);
+            }
+            QD_TRY(launch_fir(c, top, s.format, f.n_shift, ratios, d_src, src_base, src_end, soff, unit_len, stride, nu,
+                              nu * unit_len, d_out));
+            d_top = d_out;
+            pitch = unit_len;
+        } else {
+            // top-level outputs [g0, g1) as one stream; windows are cut from it at the sink's stride
+            const uint64_t g0 = soff, g1 = soff + (nu - 1) * stride + unit_len;
+            const uint64_t glen = round_up(g1 - g0, top.shape.R);
+            QD_TRY(c.ensure(c.pipe_out[j], glen * sizeof(float2) + 64));
+            float2 *d_out = static_cast<float2 *>(c.pipe_out[j].p);
+            if (f.n_lp == 1) {
+                QD_TRY(launch_fir(c, top, s.format, f.n_shift, ratios, d_src, src_base, src_end, g0, kStreamCall, kStreamCall,
+                                  1, glen, d_out));
+            } else {
+                const LpInfo &in = f.lp[0];
+                // inner outputs the outer stage reads for [g0, g1): h = g*D2 + i0_2 + j
+                const uint64_t h0 = g0 * top.D + top.i0, h1 = (g1 - 1) * top.D + top.i0 + top.L;
+                const uint64_t hlen = round_up(h1 - h0, in.shape.R);
+                QD_TRY(c.ensure(c.pipe_mid[j], hlen * sizeof(float2) + 64));
+                // keep absolute inner index 0 on a 16-byte boundary: the stream starts 8 bytes in when h0 is odd
+                float2 *d_mid = reinterpret_cast<float2 *>(static_cast<uint8_t *>(c.pipe_mid[j].p) + ((h0 & 1) ? 8 : 0));
+                QD_TRY(launch_fir(c, in, s.format, f.n_shift, ratios, d_src, src_base, src_end, h0, kStreamCall, kStreamCall, 1,
+                                  hlen, d_mid));
+                QD_TRY(launch_fir(c, top, QD_FMT_CF32, 0, nullptr, reinterpret_cast<const uint8_t *>(d_mid), h0, h1, g0,
+                                  kStreamCall, kStreamCall, 1, glen, d_out));
+            }
+            d_top = d_out;
+            pitch = stride;
+        }
         QD_TRY(c.prof_end("fk_fir (fused decode+mix+FIR-decimate)"));
-        if (on_segment) QD_TRY(on_segment(c, user, j, u0, nu, d_out));
-        QD_CUDA(cudaEventRecord(c.ev_compute[j], c.stream));
+        QD_CUDA(cudaEventRecord(c.ev_compute[j], c.stream)); // the raw staging buffer may be refilled
+        if (on_segment) QD_TRY(on_segment(c, user, j, u0, nu, d_top, pitch));
     }
+    (void)samples_sink;
     *units_done = n_full;
     return QD_OK;
 }

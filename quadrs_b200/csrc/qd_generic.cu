@@ -139,11 +139,16 @@ __device__ __forceinline__ uint32_t leaf_position(uint32_t n, uint32_t W, int n_
 enum { EPI_SPARK = 0, EPI_LEVELS = 1, EPI_TAKE = 2 };
 
 struct FftArgs {
-    const float2 *in;     // [units][in_pitch] rows of W samples
+    const float2 *in;     // cf32 windows: window u starts at in + u * in_pitch
     uint64_t in_pitch;
+    const uint8_t *raw;   // or raw capture bytes (decoded on load): window u starts at sample raw_first + u * in_pitch
+    int raw_fmt;
+    uint64_t raw_first;
+    uint64_t n_units;
     const float2 *tw;     // w(W, j), j < W
     const float *window;  // nullable (take_fft BlackmanHarris)
     uint32_t W;
+    uint32_t team;        // threads cooperating on one window
     int epi;
     float mn, mx, distinction;
     uint8_t *idx;         // SPARK [units][W]; LEVELS [units]
@@ -151,67 +156,73 @@ struct FftArgs {
     int *panic_flag;
 };
 
+// A team of `team` threads transforms one window in shared memory; a CTA holds blockDim/team windows.
 __global__ void gk_fft(FftArgs a)
 {
-    extern __shared__ float2 x[];
-    const uint32_t W = a.W;
-    const uint32_t u = blockIdx.x;
-    int logw = 31 - __clz(W);
+    extern __shared__ float2 fft_smem[];
+    const uint32_t W = a.W, TW = a.team;
+    const uint32_t wpc = blockDim.x / TW;
+    const uint32_t team = threadIdx.x / TW, lt = threadIdx.x - team * TW;
+    const uint64_t u = static_cast<uint64_t>(blockIdx.x) * wpc + team;
+    const bool active = u < a.n_units;
+    float2 *x = fft_smem + static_cast<size_t>(team) * W;
+    const int logw = 31 - __clz(W);
     const bool odd = logw & 1;
     const int n_r4 = logw >> 1;
-    const float2 *row = a.in + static_cast<size_t>(u) * a.in_pitch;
-    for (uint32_t n = threadIdx.x; n < W; n += blockDim.x) {
-        float2 v = row[n];
-        if (a.window) { // ffts.rs:64-68: Complex<f32> *= f32
-            const float w = a.window[n];
-            v = make_float2(__fmul_rn(v.x, w), __fmul_rn(v.y, w));
+    if (active) {
+        for (uint32_t n = lt; n < W; n += TW) {
+            float2 v;
+            if (a.raw) v = decode_sample(a.raw, a.raw_fmt, a.raw_first + u * a.in_pitch + n);
+            else v = a.in[u * a.in_pitch + n];
+            if (a.window) { // ffts.rs:64-68: Complex<f32> *= f32
+                const float w = a.window[n];
+                v = make_float2(__fmul_rn(v.x, w), __fmul_rn(v.y, w));
+            }
+            x[leaf_position(n, W, n_r4, odd)] = v;
         }
-        x[leaf_position(n, W, n_r4, odd)] = v;
     }
     __syncthreads();
     if (odd) { // innermost size-2 FFTs
-        for (uint32_t b = threadIdx.x; b < W / 2; b += blockDim.x) {
-            const float2 p = x[2 * b], q = x[2 * b + 1];
-            x[2 * b] = cadd(p, q);
-            x[2 * b + 1] = csub(p, q);
-        }
+        if (active)
+            for (uint32_t b = lt; b < W / 2; b += TW) {
+                const float2 p = x[2 * b], q = x[2 * b + 1];
+                x[2 * b] = cadd(p, q);
+                x[2 * b + 1] = csub(p, q);
+            }
         __syncthreads();
     }
     for (uint32_t q = odd ? 2 : 1; q < W; q <<= 2) {
         const uint32_t scale = W / (4 * q); // w(4q, j) == w(W, j * W/(4q))
-        for (uint32_t b = threadIdx.x; b < W / 4; b += blockDim.x) {
-            const uint32_t blk = b / q, k = b - blk * q;
-            float2 *base = x + static_cast<size_t>(blk) * 4 * q + k;
-            float2 t0 = base[0], t1 = base[q], t2 = base[2 * q], t3 = base[3 * q];
-            if (k != 0) {
-                t1 = cmul_tw(t1, __ldg(a.tw + k * scale));
-                t2 = cmul_tw(t2, __ldg(a.tw + 2 * k * scale));
-                t3 = cmul_tw(t3, __ldg(a.tw + 3 * k * scale));
+        if (active)
+            for (uint32_t b = lt; b < W / 4; b += TW) {
+                const uint32_t blk = b / q, k = b - blk * q;
+                float2 *base = x + static_cast<size_t>(blk) * 4 * q + k;
+                float2 t0 = base[0], t1 = base[q], t2 = base[2 * q], t3 = base[3 * q];
+                if (k != 0) {
+                    t1 = cmul_tw(t1, __ldg(a.tw + k * scale));
+                    t2 = cmul_tw(t2, __ldg(a.tw + 2 * k * scale));
+                    t3 = cmul_tw(t3, __ldg(a.tw + 3 * k * scale));
+                }
+                radix4(t0, t1, t2, t3);
+                base[0] = t0;
+                base[q] = t1;
+                base[2 * q] = t2;
+                base[3 * q] = t3;
             }
-            radix4(t0, t1, t2, t3);
-            base[0] = t0;
-            base[q] = t1;
-            base[2 * q] = t2;
-            base[3 * q] = t3;
-        }
         __syncthreads();
     }
+    if (!active) return;
     if (a.epi == EPI_LEVELS) { // fft.rs:95-97: sequential f32 sums over the natural-order halves
-        if (threadIdx.x < 2) {
-            const uint32_t lo = threadIdx.x ? W / 2 : 0, hi = threadIdx.x ? W : W / 2;
-            float s = 0.0f;
-            for (uint32_t b = lo; b < hi; b++) s = __fadd_rn(s, hypot_exact(x[b].x, x[b].y));
-            reinterpret_cast<float *>(x + W)[threadIdx.x] = s;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const float *s = reinterpret_cast<float *>(x + W);
-            a.idx[u] = s[0] < s[1] ? 0 : 1;
+        if (lt == 0) {
+            float first = 0.0f, second = 0.0f;
+            for (uint32_t b = 0; b < W / 2; b++) first = __fadd_rn(first, hypot_exact(x[b].x, x[b].y));
+            for (uint32_t b = W / 2; b < W; b++) second = __fadd_rn(second, hypot_exact(x[b].x, x[b].y));
+            a.idx[u] = first < second ? 0 : 1;
         }
         return;
     }
     const uint32_t half = W / 2;
-    for (uint32_t b = threadIdx.x; b < W; b += blockDim.x) {
+    for (uint32_t b = lt; b < W; b += TW) {
         // iter().skip(w/2).chain(iter().take(w/2)), fft.rs:48-52 / ffts.rs:72-76
         const uint32_t src = b < W - half ? b + half : b - (W - half);
         const float norm = hypot_exact(x[src].x, x[src].y);
@@ -251,6 +262,7 @@ Chain::~Chain()
     rel(flag);
     for (int j = 0; j < 2; j++) {
         rel(pipe_in[j]);
+        rel(pipe_mid[j]);
         rel(pipe_out[j]);
         rel(pipe_idx[j]);
         rel(pipe_mag[j]);
@@ -534,8 +546,9 @@ static int copy_out(Chain &c, void *dst, const void *src, size_t bytes, int spac
 }
 
 
-static void fill_fft_args(Chain &c, const SinkArgs &sink, size_t W, FftArgs *fa)
+void fill_fft_args(Chain &c, const SinkArgs &sink, size_t W, FftArgs *fa)
 {
+    memset(fa, 0, sizeof *fa);
     fa->in_pitch = W;
     fa->tw = static_cast<const float2 *>(c.twiddles.p);
     fa->window = sink.windowed ? static_cast<const float *>(c.window.p) : nullptr;
@@ -547,13 +560,20 @@ static void fill_fft_args(Chain &c, const SinkArgs &sink, size_t W, FftArgs *fa)
     fa->panic_flag = static_cast<int *>(c.flag.p);
 }
 
-static int launch_fft(Chain &c, const FftArgs &fa, uint32_t units)
+int launch_fft(Chain &c, FftArgs &fa, uint64_t units)
 {
-    const size_t smem = fa.W * sizeof(float2) + 16;
+    if (units == 0) return QD_OK;
+    const uint32_t W = fa.W;
+    const uint32_t threads = 256;
+    fa.team = std::min<uint32_t>(threads, std::max<uint32_t>(1, W / 4));
+    const uint32_t wpc = threads / fa.team;
+    fa.n_units = units;
+    const size_t smem = static_cast<size_t>(wpc) * W * sizeof(float2);
     if (smem > 48 * 1024)
         QD_CUDA(cudaFuncSetAttribute(gk_fft, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    const uint32_t threads = static_cast<uint32_t>(std::min<size_t>(256, std::max<size_t>(32, fa.W / 4)));
-    gk_fft<<<units, threads, smem, c.stream>>>(fa);
+    const uint64_t grid = (units + wpc - 1) / wpc;
+    if (grid > 0x7fffffffull) return set_error(QD_E_INVALID_ARG, "too many windows in one launch");
+    gk_fft<<<static_cast<unsigned>(grid), threads, smem, c.stream>>>(fa);
     QD_LAUNCHED();
     return QD_OK;
 }
@@ -566,16 +586,26 @@ static bool sink_has_mag(const SinkArgs &s) { return s.kind == SINK_TAKE || (s.k
 struct FastSinkCtx {
     SinkArgs *sink;
     uint64_t unit_len;
+    // windows cut straight from raw capture bytes (a chain without stages): see run_units_rawfft
+    const uint8_t *raw = nullptr;
+    int raw_fmt = 0;
+    uint64_t raw_first = 0;
 };
 
-static int fast_segment_sink(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, const float2 *d_top)
+static int fast_segment_sink(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, const float2 *d_top, uint64_t pitch)
 {
     FastSinkCtx *ctx = static_cast<FastSinkCtx *>(user);
     SinkArgs &sink = *ctx->sink;
     const size_t W = sink.width;
     const bool to_host = sink.space == QD_SPACE_HOST;
     if (sink.kind == SINK_SAMPLES) {
-        if (!to_host) return QD_OK; // the kernel wrote straight into the caller's device buffer
+        if (!to_host) {
+            // normally the kernel wrote straight into the caller's device buffer
+            if (d_top != reinterpret_cast<const float2 *>(sink.samples_out) + u0 * ctx->unit_len)
+                QD_CUDA(cudaMemcpyAsync(sink.samples_out + u0 * ctx->unit_len, d_top, nu * ctx->unit_len * sizeof(float2),
+                                        cudaMemcpyDeviceToDevice, c.stream));
+            return QD_OK;
+        }
         QD_CUDA(cudaEventRecord(c.ev_sink[j], c.stream));
         QD_CUDA(cudaStreamWaitEvent(c.d2h_stream, c.ev_sink[j], 0));
         QD_CUDA(cudaMemcpyAsync(sink.samples_out + u0 * ctx->unit_len, d_top, nu * ctx->unit_len * sizeof(float2),
@@ -586,6 +616,10 @@ static int fast_segment_sink(Chain &c, void *user, int j, uint64_t u0, uint64_t 
     FftArgs fa;
     fill_fft_args(c, sink, W, &fa);
     fa.in = d_top;
+    fa.in_pitch = pitch; // unit_len for a [units][W] matrix, the window stride for a contiguous stream
+    fa.raw = ctx->raw;
+    fa.raw_fmt = ctx->raw_fmt;
+    fa.raw_first = ctx->raw_first;
     const size_t ib = sink_idx_bytes(sink, W);
     const bool mag = sink_has_mag(sink);
     if (to_host) {
@@ -597,7 +631,7 @@ static int fast_segment_sink(Chain &c, void *user, int j, uint64_t u0, uint64_t 
         fa.idx = ib ? sink.idx_out + u0 * ib : nullptr;
         fa.mag = mag ? sink.mag_out + u0 * W : nullptr;
     }
-    QD_TRY(launch_fft(c, fa, static_cast<uint32_t>(nu)));
+    QD_TRY(launch_fft(c, fa, nu));
     if (to_host) {
         QD_CUDA(cudaEventRecord(c.ev_sink[j], c.stream));
         QD_CUDA(cudaStreamWaitEvent(c.d2h_stream, c.ev_sink[j], 0));
@@ -605,6 +639,70 @@ static int fast_segment_sink(Chain &c, void *user, int j, uint64_t u0, uint64_t 
         if (mag)
             QD_CUDA(cudaMemcpyAsync(sink.mag_out + u0 * W, fa.mag, nu * W * sizeof(float), cudaMemcpyDeviceToHost, c.d2h_stream));
         QD_CUDA(cudaEventRecord(c.ev_d2h[j], c.d2h_stream));
+    }
+    return QD_OK;
+}
+
+// `from FILE | sparkfft`: no stage between the capture and the STFT.  Windows are decoded inside the FFT
+// kernel's load, straight from the raw bytes (overlapping windows re-read them through L2); host and
+// file sources are staged in double-buffered segments like the fused FIR path.
+static int run_units_rawfft(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t W, SinkArgs &sink)
+{
+    const Source &s = c.src;
+    const uint64_t pb = pair_bytes(s.format);
+    const bool on_device = s.kind == QD_SRC_DEVICE_MEM;
+    uint64_t seg_units = n_units;
+    if (!on_device) seg_units = std::max<uint64_t>(1, c.segment_bytes / std::max<uint64_t>(1, std::min(stride, W) * pb));
+    if (sink.space == QD_SPACE_HOST)
+        seg_units = std::min<uint64_t>(seg_units, std::max<uint64_t>(1, c.scratch_budget / 2 / (W * 5)));
+    seg_units = std::min(seg_units, n_units);
+    QD_TRY(c.ensure_pipeline());
+    QD_CUDA(cudaEventRecord(c.ev_entry, c.stream));
+    QD_CUDA(cudaStreamWaitEvent(c.h2d_stream, c.ev_entry, 0));
+    QD_CUDA(cudaStreamWaitEvent(c.d2h_stream, c.ev_entry, 0));
+    FastSinkCtx ctx{&sink, W};
+    uint64_t seg = 0;
+    for (uint64_t u0 = 0; u0 < n_units; u0 += seg_units, ++seg) {
+        const int j = static_cast<int>(seg & 1);
+        const uint64_t nu = std::min(seg_units, n_units - u0);
+        const uint64_t lo = off0 + u0 * stride, hi = lo + (nu - 1) * stride + W;
+        if (lo < s.base_sample || hi > s.base_sample + s.resident_samples)
+            return set_error(QD_E_NOT_RESIDENT, "samples [%llu, %llu) requested but this source holds [%llu, %llu)",
+                             (unsigned long long)lo, (unsigned long long)hi, (unsigned long long)s.base_sample,
+                             (unsigned long long)(s.base_sample + s.resident_samples));
+        if (on_device) {
+            ctx.raw = s.data;
+            ctx.raw_first = lo - s.base_sample;
+        } else {
+            const size_t bytes = static_cast<size_t>((hi - lo) * pb);
+            QD_TRY(c.ensure(c.pipe_in[j], bytes + 64));
+            if (seg >= 2) QD_CUDA(cudaStreamWaitEvent(c.h2d_stream, c.ev_compute[j], 0));
+            if (s.kind == QD_SRC_HOST_MEM) {
+                QD_CUDA(cudaMemcpyAsync(c.pipe_in[j].p, s.data + (lo - s.base_sample) * pb, bytes, cudaMemcpyHostToDevice,
+                                        c.h2d_stream));
+            } else {
+                QD_TRY(c.ensure_pinned2(j, bytes));
+                if (seg >= 2) QD_CUDA(cudaEventSynchronize(c.ev_h2d[j]));
+                size_t done = 0;
+                while (done < bytes) {
+                    const ssize_t r = pread(s.fd, static_cast<uint8_t *>(c.h_pin2[j]) + done, bytes - done,
+                                            static_cast<off_t>(lo * pb + done));
+                    if (r <= 0) return set_error(QD_E_IO, "read %s: %s", s.path.c_str(), r < 0 ? strerror(errno) : "unexpected end of file");
+                    done += static_cast<size_t>(r);
+                }
+                QD_CUDA(cudaMemcpyAsync(c.pipe_in[j].p, c.h_pin2[j], bytes, cudaMemcpyHostToDevice, c.h2d_stream));
+            }
+            QD_CUDA(cudaEventRecord(c.ev_h2d[j], c.h2d_stream));
+            QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_h2d[j], 0));
+            ctx.raw = static_cast<const uint8_t *>(c.pipe_in[j].p);
+            ctx.raw_first = 0;
+        }
+        ctx.raw_fmt = s.format;
+        if (seg >= 2) QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_d2h[j], 0));
+        QD_TRY(c.prof_begin());
+        QD_TRY(fast_segment_sink(c, &ctx, j, u0, nu, nullptr, stride));
+        QD_TRY(c.prof_end("gk_fft (decode + STFT + magnitude + bucket)"));
+        QD_CUDA(cudaEventRecord(c.ev_compute[j], c.stream));
     }
     return QD_OK;
 }
@@ -768,12 +866,18 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
 
     uint64_t produced = 0, done = 0;
     bool used_pipeline = false;
-    if (!offsets && c.use_fast) {
+    if (!offsets && c.use_fast && fft_sink && c.stages.empty() && c.src.kind != QD_SRC_GEN) {
+        QD_TRY(run_units_rawfft(c, off0, stride, n_units, unit_len, sink));
+        done = produced = n_units;
+        QD_CUDA(cudaEventRecord(c.ev_exit, c.d2h_stream));
+        QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_exit, 0));
+    } else if (!offsets && c.use_fast) {
         FastSinkCtx ctx{&sink, unit_len};
         float2 *direct = (sink.kind == SINK_SAMPLES && sink.space == QD_SPACE_DEVICE)
                              ? reinterpret_cast<float2 *>(sink.samples_out)
                              : nullptr;
-        QD_TRY(run_units_fast(c, off0, stride, n_units, unit_len, direct, fast_segment_sink, &ctx, &done));
+        QD_TRY(run_units_fast(c, off0, stride, n_units, unit_len, sink.kind == SINK_SAMPLES, direct, fast_segment_sink, &ctx,
+                              &done));
         used_pipeline = done > 0;
         produced = sink.kind == SINK_SAMPLES ? done * unit_len : done;
         if (used_pipeline) {

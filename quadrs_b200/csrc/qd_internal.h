@@ -151,7 +151,7 @@ struct Chain {
     cudaEvent_t ev_entry = nullptr, ev_exit = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_sink[2] = {nullptr, nullptr},
                 ev_d2h[2] = {nullptr, nullptr};
-    Buf pipe_in[2], pipe_out[2], pipe_idx[2], pipe_mag[2];
+    Buf pipe_in[2], pipe_mid[2], pipe_out[2], pipe_idx[2], pipe_mag[2];
     void *h_pin2[2] = {nullptr, nullptr};
     size_t h_pin2_cap[2] = {0, 0};
     int ensure_pipeline();
@@ -205,9 +205,11 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
 // Output of segment units [u0, u0+nu) is [nu][unit_len] cf32 at d_direct + u0*unit_len when d_direct
 // is given, else in a library staging buffer; on_segment (nullable) is called after each segment's
 // kernel has been enqueued on c.stream, with j = staging slot.
-typedef int (*FastSegmentFn)(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, const float2 *d_top);
-int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_direct,
-                   FastSegmentFn on_segment, void *user, uint64_t *units_done);
+// d_top/pitch: unit u of the segment starts at d_top + u*pitch (pitch = unit_len for a [units][n] matrix,
+// = stride when the top stage was materialised as one contiguous stream).
+typedef int (*FastSegmentFn)(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, const float2 *d_top, uint64_t pitch);
+int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, bool samples_sink,
+                   float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done);
 
 int synth_fill(const qd_synth *p, int format, uint64_t first, uint64_t n, void *d_out, int device, cudaStream_t st);
 

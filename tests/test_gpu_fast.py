@@ -28,6 +28,18 @@ CASES = [
     (O.CS8, [("lowpass", 1_000_000, 8, 37)], ("write", 64)),  # odd filter length: NaN taps, still the same order
     (O.CS8, [("shift", 3_000_000), ("lowpass", 500_000, 16, 100)], ("spark", 32, 7, (0.01, 1.0))),
     (O.CU8, [("shift", 3_000_000), ("lowpass", 500_000, 32, 40)], ("spark", 4, 2, (0.01, 1.0))),
+    # two-stage lowpass shared as streams (config 5 shape): the outer stage never sees the inner truncated tail
+    (O.CF32, [("lowpass", 5_000_000, 8, 40), ("lowpass", 125_000, 32, 40)], ("spark", 4, 2, (0.001, 0.01))),
+    (O.CS8, [("shift", 1_000_000), ("lowpass", 5_000_000, 8, 40), ("lowpass", 125_000, 32, 40)], ("write", 0x1000)),
+    (O.CS16, [("lowpass", 5_000_000, 4, 24), ("lowpass", 1_000_000, 16, 30)], ("spark", 32, 8, (0.1, 10.0))),
+    # single lowpass without truncated positions (D >= L - L/2): overlapping windows cut from one stream
+    (O.CS16, [("lowpass", 1_000_000, 8, 8)], ("spark", 16, 3, (0.1, 10.0))),
+    (O.CS8, [("shift", -2_000_000), ("lowpass", 3_000_000, 32, 40)], ("spark", 8, 1, (0.01, 1.0))),
+    # no stage at all: windows decoded straight from the capture bytes
+    (O.CU8, [], ("spark", 4096, 1024, (2.0, 500.0))),  # config 3 shape
+    (O.CF32, [], ("spark", 64, 16, (0.01, 3.0))),
+    (O.CS8, [], ("spark", 4, 1, (0.01, 1.0))),
+    (O.CS16, [], ("spark", 2, 2, None)),
 ]
 
 
