@@ -11,6 +11,10 @@ from .chain import (CF32, CS8, CU8, CS16, EXACT, FAST, Samples, do_write, format
 from .shard import plan_shards, shard_plan
 from .synth import make_synth, synth_fill_device, tone_step
 
+# FAST arithmetic (block-anchored f64 phase + FMA FIR) is validated against the oracle at 1e-5 for cs8/cf32
+# (tests/test_gpu_fast.py::test_fast_mode_*); bench.py uses it for those formats with a cf32 sink.
+FAST_READY = True
+
 __all__ = [
     "QdError", "build", "CF32", "CS8", "CU8", "CS16", "EXACT", "FAST", "Samples", "do_write",
     "format_from_extension", "format_row", "freq_levels", "spark_fft", "take_fft", "plan_shards", "shard_plan",

@@ -13,6 +13,7 @@
 // opaque 1.0: ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2, which would change the
 // rounding) and so is bit-identical to the reference's `acc += x * f`; FAST mode uses one FFMA2.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include <unistd.h>
@@ -50,6 +51,9 @@ struct FirArgs {
     uint32_t raw_cap; // bytes per raw staging buffer
     float2 *out;      // [n_units][n_call]
     float2 one;       // (1, 1), opaque to ptxas
+    // FAST mode NCO: all leading shifts merged into one rotation of ratio_sum per sample
+    float2 rot[4];    // e^{i k ratio_sum}, k = 0..3 (k = 0 unused)
+    float2 rot_step;  // e^{i 4*NT ratio_sum}: from one group of a thread to its next
 };
 
 // ---------------------------------------------------------------------------- PTX helpers
@@ -210,6 +214,12 @@ __device__ __forceinline__ TileGeo tile_geo(const FirArgs &a, uint64_t tile)
 // fixed position in the group the half-warp writes to consecutive physical rows: conflict-free.
 // ALIGNED: the tile's first sample sits on a group boundary (lead % 4 == 0), the common case, and the
 // four stores of a group are one base address plus compile-time offsets.
+// FAST mode complex multiply: contraction allowed
+__device__ __forceinline__ float2 cmul_fast(float2 a, float2 b)
+{
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+
 __device__ __forceinline__ float2 mix_exact(float2 v, double nd, double ratio, const FirArgs &a)
 {
     double c, sn;
@@ -217,7 +227,7 @@ __device__ __forceinline__ float2 mix_exact(float2 v, double nd, double ratio, c
     return cmul_exact(v, make_float2(static_cast<float>(c), static_cast<float>(sn)));
 }
 
-template <int FMT, int D, int R, int NT, bool ALIGNED>
+template <int FMT, int D, int R, int NT, bool ALIGNED, bool FASTMIX>
 __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
                                             uint64_t n_tile0, float2 *__restrict__ X, int tid)
 {
@@ -228,6 +238,22 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
     const double base_d = __ull2double_rn(n_tile0 - lead);
     const int n_shift = a.n_shift;
     const float2 one = a.one;
+    // FAST: the phase is evaluated in f64 exactly as the reference does it (shift.rs:49) once per thread and
+    // tile, at the thread's first sample, and carried forward by f32 rotations (<= 8 steps of 4*NT samples)
+    float2 ph_g = make_float2(1.0f, 0.0f);
+    if (FASTMIX && n_shift) {
+        // anchor = e^{i * (exact n*ratio)}: the f64 phase p = fl64(n*ratio) is off the exact product by
+        // delta = -fma(n, ratio, -p), removed here and re-applied per sample below
+        const double nd = __dadd_rn(base_d, static_cast<double>(4 * tid));
+        for (int s = 0; s < n_shift; s++) {
+            const double p = __dmul_rn(nd, a.ratio[s]);
+            const float e = static_cast<float>(fma(nd, a.ratio[s], -p));
+            double c, sn;
+            sincos_f64k(p, a.sincos, a.k, c, sn);
+            const float cf = static_cast<float>(c), sf = static_cast<float>(sn);
+            ph_g = cmul_fast(ph_g, make_float2(fmaf(-e, sf, cf), fmaf(e, cf, sf)));
+        }
+    }
     for (uint32_t grp = tid; grp < n_groups; grp += NT) {
         uint32_t w[8];
         if (FMT == QD_FMT_CF32) {
@@ -247,7 +273,25 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
         float2 v[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) v[i] = decode_in_group<FMT>(w, i, one);
-        if (n_shift) {
+        if (FASTMIX) {
+            if (n_shift) {
+                // the reference's phase is fl64(n*ratio) (shift.rs:49): its rounding error against the exact
+                // product, e = n*ratio - p, is recovered exactly by one FMA and applied as a small rotation
+                const double nd0 = __dadd_rn(base_d, static_cast<double>(g4));
+                const double r0 = a.ratio[0];
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const double nd = __dadd_rn(nd0, static_cast<double>(i));
+                    float e = static_cast<float>(fma(nd, r0, -__dmul_rn(nd, r0)));
+                    if (n_shift > 1)
+                        for (int s = 1; s < n_shift; s++) e += static_cast<float>(fma(nd, a.ratio[s], -__dmul_rn(nd, a.ratio[s])));
+                    float2 ph = i == 0 ? ph_g : cmul_fast(ph_g, a.rot[i]);
+                    ph = make_float2(fmaf(e, ph.y, ph.x), fmaf(-e, ph.x, ph.y)); // * (1 - i e) = * e^{i delta}
+                    v[i] = cmul_fast(v[i], ph);
+                }
+                ph_g = cmul_fast(ph_g, a.rot_step);
+            }
+        } else if (n_shift) {
             const double nd0 = __dadd_rn(base_d, static_cast<double>(g4));
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -413,17 +457,17 @@ __global__ void __launch_bounds__(NT, 2) fk_fir(const __grid_constant__ FirArgs 
                                         : reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
             if ((lead & 3) == 0) {
                 switch (a.fmt) {
-                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                default: decode_tile<QD_FMT_CF32, D, R, NT, true>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                default: decode_tile<QD_FMT_CF32, D, R, NT, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
                 }
             } else {
                 switch (a.fmt) {
-                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                default: decode_tile<QD_FMT_CF32, D, R, NT, false>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                default: decode_tile<QD_FMT_CF32, D, R, NT, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
                 }
             }
         }
@@ -609,6 +653,13 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     a.raw_cap = fmt == QD_FMT_CF32 ? 0 : static_cast<uint32_t>(((span_max * pb + 15) / 16) * 16 + 32);
     a.out = d_out;
     a.one = make_float2(1.0f, 1.0f);
+    {
+        double rsum = 0.0;
+        for (int i = 0; i < n_shift; i++) rsum += ratios[i];
+        for (int k = 0; k < 4; k++) a.rot[k] = make_float2(static_cast<float>(cos(k * rsum)), static_cast<float>(sin(k * rsum)));
+        const double step = 4.0 * lp.shape.NT * rsum;
+        a.rot_step = make_float2(static_cast<float>(cos(step)), static_cast<float>(sin(step)));
+    }
     FirTaps taps;
     memset(&taps, 0, sizeof taps);
     for (uint32_t j = 0; j < a.L; j++) taps.t[j] = make_float2(st.taps[j], st.taps[j]);

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import oracle_lib as O
-from helpers import assert_bit_equal, gpu_chain, kept_only, oracle_chain, synth_raw
+from helpers import assert_bit_equal, gpu_chain, kept_only, oracle_chain, rel_err, synth_raw
 
 pytestmark = pytest.mark.gpu
 
@@ -220,3 +220,79 @@ def test_full_size_config4_shape_sampled_rows(Q):
     want = _oracle_rows_from_device(Q, torch, d_in, O.CS16, rate, total, base, st, 128, 128, (0.5, 50.0), rows, 128 * 16 + 800)
     for r, (widx, _) in zip(rows, want):
         assert np.array_equal(idx[r - first], widx), f"row {r}"
+
+
+# ---------------------------------------------------------------- FAST arithmetic mode
+FAST_CASES = [
+    (O.CS8, 20_000_000, [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)], 0),                      # config 2
+    (O.CS8, 20_000_000, [("shift", 9_999_999), ("lowpass", 1_000_000, 8, 40)], 2**30 - 600_000),        # near Nyquist, n ~ 2^30
+    (O.CF32, 21_000_000, [("shift", 280_000), ("lowpass", 200_000, 32, 400)], 0),                       # config 1
+    (O.CF32, 400_000_000, [("shift", -150_000_000), ("shift", 199_999_999), ("lowpass", 20_000_000, 8, 40)], 2**34 - 600_000 - 2**34 % 0x8000),
+    (O.CF32, 400_000_000, [("lowpass", 20_000_000, 8, 40), ("lowpass", 500_000, 32, 40)], 0),           # config 5
+]
+
+
+@pytest.mark.parametrize("fmt,rate,stages,base", FAST_CASES)
+def test_fast_mode_within_1e5_of_the_oracle(Q, fmt, rate, stages, base):
+    """north_star tolerance: cf32 samples within 1e-5 relative (max-norm per 0x1000-sample chunk).  FAST keeps
+    integer decode exact, evaluates the f64 phase once per thread and tile, and contracts the FIR to FMA."""
+    n = 500_000 if _mult(stages) <= 8 else 3_000_000
+    total = base + n
+    raw, _ = synth_raw(fmt, n, first=base, rate=rate)
+    fast = gpu_chain(raw, fmt, rate, stages, base, total if base else 0, precision=Q.FAST)
+    first = -(-base // (0x1000 * _mult(stages)))
+    with kept_only():
+        want, _ = oracle_chain(raw, fmt, rate, stages, base, total if base else 0).write_mem(first_chunk=first, max_chunks=10)
+    got, _ = fast.write_mem(first_chunk=first, max_chunks=10)
+    assert len(got) == len(want) and len(want) >= 8_000
+    worst = 0.0
+    for c in range(0, len(want), 0x1000):
+        worst = max(worst, rel_err(got[c : c + 0x1000], want[c : c + 0x1000]))
+    print(f"FAST worst chunk rel err {worst:.3e}")
+    assert worst <= 1e-5, worst
+
+
+def _mult(stages):
+    m = 1
+    for st in stages:
+        if st[0] == "lowpass":
+            m *= st[2]
+    return m
+
+
+def test_fast_mode_is_refused_for_offset_formats(Q):
+    raw, _ = synth_raw(O.CS16, 10_000)
+    for fmt in (O.CS16, O.CU8):
+        with pytest.raises(Q.QdError) as e:
+            gpu_chain(raw, fmt, 20_000_000, [("shift", 1_000_000), ("lowpass", 1_000_000, 8, 40)], precision=Q.FAST)
+        assert e.value.code == Q._lib.E_INVALID_ARG and "1e-5" in e.value.msg
+
+
+def test_fast_mode_full_size_config2_against_exact(Q):
+    """The bench workload itself (2^30 cs8 samples, config 2): every 0x1000-sample chunk of the FAST output is
+    within 1e-5 (max-norm relative) of the bit-exact EXACT output, which the tests above tie to the oracle."""
+    import torch
+
+    n = 2**30
+    fmt, rate = Q.CS8, 20_000_000
+    synth = Q.make_synth(0x5EED0002, [(Q.tone_step(1.6e6, rate), 45, 0), (Q.tone_step(-4.1e6, rate), 30, 0),
+                                      (Q.tone_step(0.3e6, rate), 20, 3000)], 6)
+    d_in = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    Q.synth_fill_device(synth, fmt, 0, n, d_in.data_ptr())
+    torch.cuda.synchronize()
+    chunks = 32767
+    outs = []
+    for prec in (Q.EXACT, Q.FAST):
+        chain = Q.Samples.from_device(d_in.data_ptr(), 2 * n, fmt, rate, keep=(d_in,)).shift(1_500_000)
+        chain = chain.lowpass(1_000_000, 8, 40).with_precision(prec)
+        d_out = torch.zeros(2 * chunks * 0x1000, dtype=torch.float32, device="cuda")
+        got_n, rc = chain.write_into(0x1000, 0, chunks, d_out.data_ptr(), chunks * 0x1000, Q._lib.SPACE_DEVICE)
+        chain.synchronize()
+        assert got_n == chunks * 0x1000 and rc == 0
+        outs.append(torch.view_as_complex(d_out.view(-1, 2)).view(chunks, 0x1000))
+    exact, fast = outs
+    err = (fast - exact).abs().amax(dim=1) / exact.abs().amax(dim=1)
+    worst = float(err.max())
+    print(f"FAST vs EXACT over 2^30 samples: worst chunk rel err {worst:.3e}, mean {float(err.mean()):.3e}")
+    assert worst <= 1e-5, worst
+    assert not torch.equal(exact, fast)
