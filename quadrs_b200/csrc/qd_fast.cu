@@ -3,7 +3,8 @@
 // Canonical chain: From(cs8|cu8|cs16|cf32) -> Shift* -> LowPass, feeding do_write chunks, read_at
 // units or sparkfft windows (samples.rs:72-93 -> shift.rs:46-54 -> filter.rs:54-124).  Each raw sample
 // crosses HBM once: a persistent CTA stages a tile of raw bytes plus its (taps-1) halo in shared
-// memory with a 1-D bulk async copy (TMA, cp.async.bulk + mbarrier, double buffered), decodes and
+// memory with a 1-D bulk async copy (TMA, cp.async.bulk + mbarrier; the next tile's copy is in flight while
+// the current tile is filtered), decodes and
 // mixes it once into a polyphase shared-memory layout, then computes ONLY the kept outputs, each
 // thread holding R consecutive outputs in registers so every staged sample is reused from registers.
 //
@@ -351,9 +352,14 @@ __device__ __forceinline__ void general_block(const float2 *__restrict__ X, int 
         if (qb < 0 || qb >= Q) continue;
         const int pmax = min(plim, qb == Q - 1 ? Lrem : D);
         const float2 *tp = taps.t + qb * D;
+        if (pmax >= D) {
 #pragma unroll
-        for (int p = 0; p < D; p++)
-            if (p < pmax) acc[r] = mac<EXACT>(acc[r], v[p], tp[p], one);
+            for (int p = 0; p < D; p++) acc[r] = mac<EXACT>(acc[r], v[p], tp[p], one);
+        } else {
+#pragma unroll
+            for (int p = 0; p < D; p++)
+                if (p < pmax) acc[r] = mac<EXACT>(acc[r], v[p], tp[p], one);
+        }
     }
 }
 
@@ -379,14 +385,17 @@ __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid
 }
 
 template <int D, int R, int NT, bool EXACT>
-__device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int tid, int Q, int Lrem, int s_total,
+__device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int tid, int Q, int Lrem, int s_end,
                                             const FirTaps &taps, float2 one, float2 (&acc)[R])
 {
+    // s_end: the thread's samples s >= s_end do not exist for this read (truncated tail, filter.rs:68-71);
+    // untruncated threads pass (R-1)*D + L
     const int NB = R - 1 + Q;
+    const int full = min(Q - 1, s_end / D); // blocks below this are complete and carry full tap blocks
     int b = 0;
-    for (; b < min(R - 1, NB); ++b) general_block<D, R, NT, EXACT>(X, tid, b, s_total, Q, Lrem, taps, one, acc);
+    for (; b < min(R - 1, NB); ++b) general_block<D, R, NT, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
     // steady state: blocks R-1 <= b < Q-1 feed every output with a full tap block
-    for (; b + R <= Q - 1; b += R) {
+    for (; b + R <= full; b += R) {
 #pragma unroll
         for (int k = 0; k < R; k++) {
             float2 v[D];
@@ -399,7 +408,7 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
             }
         }
     }
-    for (; b < NB; ++b) general_block<D, R, NT, EXACT>(X, tid, b, s_total, Q, Lrem, taps, one, acc);
+    for (; b < NB; ++b) general_block<D, R, NT, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
 }
 
 template <int D, int R, int NT, bool EXACT, int LS>
@@ -430,30 +439,26 @@ __global__ void __launch_bounds__(NT, 2) fk_fir(const __grid_constant__ FirArgs 
         const uint8_t *abeg = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
         const uintptr_t gend = reinterpret_cast<uintptr_t>(gbeg + n_dec * pb);
         const uint32_t bytes = static_cast<uint32_t>(((gend + 15) & ~uintptr_t(15)) - reinterpret_cast<uintptr_t>(abeg));
-        mbar_expect_tx(&mbar[buf], bytes);
-        bulk_g2s(raw0 + static_cast<size_t>(buf) * a.raw_cap, abeg, bytes, &mbar[buf]);
+        (void)buf;
+        mbar_expect_tx(&mbar[0], bytes);
+        bulk_g2s(raw0, abeg, bytes, &mbar[0]);
     };
 
     uint64_t it = 0;
     if (staged && tid == 0 && blockIdx.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, blockIdx.x), 0);
 
     for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const int buf = static_cast<int>(it & 1);
         const TileGeo g = tile_geo<D, Gm::T_OUT>(a, tile);
         const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + a.L;
         const uint32_t n_dec = static_cast<uint32_t>(min(span, a.src_end - g.n_tile0));
         const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * pb;
         const uint32_t lead = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gbeg) & 15) / pb;
 
-        if (staged) {
-            // prefetch the next tile's bytes while this one is decoded and filtered
-            if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x), buf ^ 1);
-            mbar_wait(&mbar[buf], static_cast<uint32_t>((it >> 1) & 1));
-        }
+        if (staged) mbar_wait(&mbar[0], static_cast<uint32_t>(it & 1));
 
         // ---- decode + mix once per sample, into the polyphase layout ------------------------------
         {
-            const uint8_t *raw = staged ? raw0 + static_cast<size_t>(buf) * a.raw_cap
+            const uint8_t *raw = staged ? raw0
                                         : reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
             if ((lead & 3) == 0) {
                 switch (a.fmt) {
@@ -472,6 +477,8 @@ __global__ void __launch_bounds__(NT, 2) fk_fir(const __grid_constant__ FirArgs 
             }
         }
         __syncthreads();
+        // the raw bytes are consumed: fetch the next tile's while this one is filtered
+        if (staged && tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x), 0);
 
         // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
         if (static_cast<uint32_t>(R * tid) < g.cnt) {
@@ -491,12 +498,11 @@ __global__ void __launch_bounds__(NT, 2) fk_fir(const __grid_constant__ FirArgs 
 #pragma unroll
             for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f); // Complex::zero(), filter.rs:112
 
-            if (s_lim >= s_total) {
-                if (LS > 0) fir_static<D, R, NT, EXACT, (LS > 0 ? LS : 1)>(X, tid, taps, one, acc);
-                else fir_dynamic<D, R, NT, EXACT>(X, tid, Q, Lrem, s_total, taps, one, acc);
-            } else { // the tail of a read: outputs whose taps run past the end of the unit's raw buffer
-                const int s_end = static_cast<int>(s_lim);
-                for (int b = 0; b < R - 1 + Q; ++b) general_block<D, R, NT, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
+            if (LS > 0 && s_lim >= s_total) {
+                fir_static<D, R, NT, EXACT, (LS > 0 ? LS : 1)>(X, tid, taps, one, acc);
+            } else { // also the tail of a read: outputs whose taps run past the end of the unit's raw buffer
+                const int s_end = static_cast<int>(min(static_cast<int64_t>(s_total), s_lim));
+                fir_dynamic<D, R, NT, EXACT>(X, tid, Q, Lrem, s_end, taps, one, acc);
             }
             float2 *o = a.out + g.out0 + static_cast<uint64_t>(R * tid);
             if (R % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
@@ -534,7 +540,7 @@ template <int D, int R, int NT, bool EXACT, int LS>
 static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
 {
     using Gm = FirGeom<D, R, NT>;
-    const size_t smem = 16 + Gm::X_BYTES + 2 * static_cast<size_t>(a.raw_cap);
+    const size_t smem = 16 + Gm::X_BYTES + static_cast<size_t>(a.raw_cap);
     if (smem > 227 * 1024) return set_error(QD_E_INVALID_ARG, "internal: fused FIR tile needs %zu bytes of shared memory", smem);
     const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
     const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, 4)));
