@@ -65,7 +65,7 @@ typedef enum {
 /* ---- sources: Operation::From / Operation::Gen, src/lib.rs:26-29,54-58,89-101 ---- */
 typedef enum {
     QD_SRC_HOST_MEM = 0,   /* raw capture bytes in host memory (what SampleFile preads, samples.rs:72-93) */
-    QD_SRC_DEVICE_MEM = 1, /* the same bytes already resident in HBM */
+    QD_SRC_DEVICE_MEM = 1, /* the same bytes already resident in HBM (pointer aligned to one sample) */
     QD_SRC_FILE = 2,       /* path; the library preads it */
     QD_SRC_GEN = 3         /* gen.rs */
 } qd_source_kind;

@@ -109,6 +109,9 @@ static int describe(const qd_source *src, const qd_stage *stages, size_t n_stage
             if (!src->data && src->n_bytes) return set_error(QD_E_INVALID_ARG, "memory source without data");
             s.data = static_cast<const uint8_t *>(src->data);
             s.n_bytes = src->n_bytes;
+            if (s.kind == QD_SRC_DEVICE_MEM && reinterpret_cast<uintptr_t>(src->data) % pb != 0)
+                return set_error(QD_E_INVALID_ARG, "device capture pointer must be aligned to one sample (%llu bytes)",
+                                 (unsigned long long)pb);
         } else {
             return set_error(QD_E_INVALID_ARG, "unknown source kind %d", s.kind);
         }

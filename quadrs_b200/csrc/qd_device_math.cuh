@@ -11,10 +11,19 @@
 namespace qd {
 
 // ---- FileFormat::to_f32, lib.rs:241-255 ------------------------------------------------------
-// The divide must be the correctly rounded IEEE divide; multiplying by a reciprocal is not bit-exact.
-__device__ __forceinline__ float dec_s8(int v) { return __fdiv_rn(static_cast<float>(v), 127.0f); }
-__device__ __forceinline__ float dec_u8(unsigned v) { return __fsub_rn(__fdiv_rn(static_cast<float>(v), 255.0f), 127.5f); }
-__device__ __forceinline__ float dec_s16(int v) { return __fsub_rn(__fdiv_rn(static_cast<float>(v), 65535.0f), 32767.5f); }
+// The quotient must be the correctly rounded IEEE quotient; multiplying by a reciprocal alone is not
+// bit-exact.  div_exact gets it without the IEEE divide sequence: q0 = x*c, r = fma(-q0, den, x),
+// q = fma(r, c, q0) with c = fl(1/den) -- verified exhaustively on the host for every i8 / 127, u8 / 255
+// and i16 / 65535 (tests/test_decode_trick.py).
+__device__ __forceinline__ float div_exact(float x, float den, float c)
+{
+    const float q0 = __fmul_rn(x, c);
+    const float r = __fmaf_rn(-q0, den, x);
+    return __fmaf_rn(r, c, q0);
+}
+__device__ __forceinline__ float dec_s8(int v) { return div_exact(static_cast<float>(v), 127.0f, 1.0f / 127.0f); }
+__device__ __forceinline__ float dec_u8(unsigned v) { return __fsub_rn(div_exact(static_cast<float>(v), 255.0f, 1.0f / 255.0f), 127.5f); }
+__device__ __forceinline__ float dec_s16(int v) { return __fsub_rn(div_exact(static_cast<float>(v), 65535.0f, 1.0f / 65535.0f), 32767.5f); }
 
 // One sample (I first, Q second: lib.rs:234-237) at index i of a raw byte stream.
 __device__ __forceinline__ float2 decode_sample(const uint8_t *__restrict__ raw, int fmt, uint64_t i)

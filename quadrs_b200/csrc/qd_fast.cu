@@ -113,16 +113,6 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 }
 
 // ---------------------------------------------------------------------------- exact integer decode
-// (float)v / den with the correctly rounded quotient, without the IEEE divide sequence:
-// q0 = x*c, r = fma(-q0, den, x), q = fma(r, c, q0), c = fl(1/den).  Verified exhaustively on the
-// host for every i8 / 127, u8 / 255 and i16 / 65535 (tests/test_decode_trick.py).
-__device__ __forceinline__ float div_exact(float x, float den, float c)
-{
-    const float q0 = __fmul_rn(x, c);
-    const float r = __fmaf_rn(-q0, den, x);
-    return __fmaf_rn(r, c, q0);
-}
-
 // the same, on an (I, Q) pair at once
 __device__ __forceinline__ float2 div_exact2(float2 x, float den, float c)
 {
@@ -769,30 +759,30 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
             src_base = s.base_sample;
             src_end = s.base_sample + s.resident_samples;
         } else {
-            // stage [lo8, hi) where lo8 keeps absolute sample 0 on a 16-byte boundary of the buffer
-            const uint64_t lo8 = lo & ~uint64_t(7);
-            const size_t bytes = static_cast<size_t>((hi - lo8) * pb);
+            // stage [lo, hi) at the byte offset that keeps absolute sample 0 on a 16-byte boundary
+            const size_t skew = static_cast<size_t>((lo * pb) & 15);
+            const size_t bytes = static_cast<size_t>((hi - lo) * pb);
             QD_TRY(c.ensure(c.pipe_in[j], bytes + 64));
+            uint8_t *dst = static_cast<uint8_t *>(c.pipe_in[j].p) + skew;
             if (seg >= 2) QD_CUDA(cudaStreamWaitEvent(c.h2d_stream, c.ev_compute[j], 0)); // buffer j is free again
             if (s.kind == QD_SRC_HOST_MEM) {
-                QD_CUDA(cudaMemcpyAsync(c.pipe_in[j].p, s.data + (lo8 - s.base_sample) * pb, bytes, cudaMemcpyHostToDevice,
-                                        c.h2d_stream));
+                QD_CUDA(cudaMemcpyAsync(dst, s.data + (lo - s.base_sample) * pb, bytes, cudaMemcpyHostToDevice, c.h2d_stream));
             } else {
                 QD_TRY(c.ensure_pinned2(j, bytes));
                 if (seg >= 2) QD_CUDA(cudaEventSynchronize(c.ev_h2d[j])); // pinned buffer j has been consumed
                 size_t done = 0;
                 while (done < bytes) {
                     const ssize_t r = pread(s.fd, static_cast<uint8_t *>(c.h_pin2[j]) + done, bytes - done,
-                                            static_cast<off_t>(lo8 * pb + done));
+                                            static_cast<off_t>(lo * pb + done));
                     if (r <= 0) return set_error(QD_E_IO, "read %s: %s", s.path.c_str(), r < 0 ? strerror(errno) : "unexpected end of file");
                     done += static_cast<size_t>(r);
                 }
-                QD_CUDA(cudaMemcpyAsync(c.pipe_in[j].p, c.h_pin2[j], bytes, cudaMemcpyHostToDevice, c.h2d_stream));
+                QD_CUDA(cudaMemcpyAsync(dst, c.h_pin2[j], bytes, cudaMemcpyHostToDevice, c.h2d_stream));
             }
             QD_CUDA(cudaEventRecord(c.ev_h2d[j], c.h2d_stream));
             QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_h2d[j], 0));
-            d_src = static_cast<const uint8_t *>(c.pipe_in[j].p);
-            src_base = lo8;
+            d_src = static_cast<const uint8_t *>(c.pipe_in[j].p) + ((lo * pb) & 15);
+            src_base = lo;
             src_end = hi;
         }
         if (seg >= 2) QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_d2h[j], 0)); // output staging j drained

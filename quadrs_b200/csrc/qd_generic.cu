@@ -136,26 +136,6 @@ __device__ __forceinline__ uint32_t leaf_position(uint32_t n, uint32_t W, int n_
     return p;
 }
 
-enum { EPI_SPARK = 0, EPI_LEVELS = 1, EPI_TAKE = 2 };
-
-struct FftArgs {
-    const float2 *in;     // cf32 windows: window u starts at in + u * in_pitch
-    uint64_t in_pitch;
-    const uint8_t *raw;   // or raw capture bytes (decoded on load): window u starts at sample raw_first + u * in_pitch
-    int raw_fmt;
-    uint64_t raw_first;
-    uint64_t n_units;
-    const float2 *tw;     // w(W, j), j < W
-    const float *window;  // nullable (take_fft BlackmanHarris)
-    uint32_t W;
-    uint32_t team;        // threads cooperating on one window
-    int epi;
-    float mn, mx, distinction;
-    uint8_t *idx;         // SPARK [units][W]; LEVELS [units]
-    float *mag;           // SPARK nullable / TAKE [units][W]
-    int *panic_flag;
-};
-
 // A team of `team` threads transforms one window in shared memory; a CTA holds blockDim/team windows.
 __global__ void gk_fft(FftArgs a)
 {
@@ -564,6 +544,11 @@ int launch_fft(Chain &c, FftArgs &fa, uint64_t units)
 {
     if (units == 0) return QD_OK;
     const uint32_t W = fa.W;
+    if (c.use_fast && fa.epi == EPI_SPARK && W <= 4096 && !fa.window) {
+        bool handled = false;
+        QD_TRY(launch_stft_fast(c, fa, units, &handled));
+        if (handled) return QD_OK;
+    }
     const uint32_t threads = 256;
     fa.team = std::min<uint32_t>(threads, std::max<uint32_t>(1, W / 4));
     const uint32_t wpc = threads / fa.team;
@@ -701,7 +686,7 @@ static int run_units_rawfft(Chain &c, uint64_t off0, uint64_t stride, uint64_t n
         if (seg >= 2) QD_CUDA(cudaStreamWaitEvent(c.stream, c.ev_d2h[j], 0));
         QD_TRY(c.prof_begin());
         QD_TRY(fast_segment_sink(c, &ctx, j, u0, nu, nullptr, stride));
-        QD_TRY(c.prof_end("gk_fft (decode + STFT + magnitude + bucket)"));
+        QD_TRY(c.prof_end("fk_stft (decode + STFT + magnitude + bucket)"));
         QD_CUDA(cudaEventRecord(c.ev_compute[j], c.stream));
     }
     return QD_OK;

@@ -103,3 +103,68 @@ uint64_t f64_as_u64(double v)
 }
 
 } // namespace qd
+
+namespace qd {
+
+// fft.rs:53-60 on the host, with the panic zone reported as 9
+static int glyph_host(float norm, float mn, float mx)
+{
+    if (norm < mn) return 0;
+    if (norm >= mx) return 8;
+    const float distinction = (mx - mn) / 7.0f;
+    const float q = (norm - mn) / distinction;
+    if (!(q > 0.0f)) return 1;
+    if (q >= 7.0f) return 9;
+    return 1 + static_cast<int>(q);
+}
+
+// The glyph is a non-decreasing step function of the magnitude in the order ' ', 7 bars, panic zone, full
+// block; the magnitude (float)sqrt(s) is a non-decreasing function of s = fl64(re^2 + im^2).  So each
+// boundary is ONE f64 threshold on s, found by bisection over bit patterns with the exact host arithmetic.
+bool spark_thresholds(float mn, float mx, double thr[9])
+{
+    auto rank = [&](float norm) {
+        const int g = glyph_host(norm, mn, mx);
+        return g <= 7 ? g : (g == 9 ? 8 : 9);
+    };
+    auto f32_from_bits = [](uint32_t b) {
+        float f;
+        memcpy(&f, &b, 4);
+        return f;
+    };
+    auto f64_from_bits = [](uint64_t b) {
+        double d;
+        memcpy(&d, &b, 8);
+        return d;
+    };
+    const uint32_t inf32 = 0x7f800000u;
+    const uint64_t inf64 = 0x7ff0000000000000ull;
+    for (int r = 1; r <= 9; r++) {
+        // smallest non-negative float (by bit pattern) with rank >= r, or none
+        if (rank(f32_from_bits(inf32)) < r) {
+            thr[r - 1] = f64_from_bits(0x7ff8000000000000ull); // NaN: no s compares >= it
+            continue;
+        }
+        uint32_t lo = 0, hi = inf32; // hi satisfies
+        if (rank(f32_from_bits(0)) >= r) hi = 0;
+        while (lo < hi) {
+            const uint32_t mid = lo + (hi - lo) / 2;
+            if (rank(f32_from_bits(mid)) >= r) hi = mid;
+            else lo = mid + 1;
+        }
+        const float nb = f32_from_bits(hi);
+        // smallest non-negative double s with (float)sqrt(s) >= nb
+        uint64_t a = 0, b = inf64;
+        auto ok = [&](uint64_t bits) { return static_cast<float>(sqrt(f64_from_bits(bits))) >= nb; };
+        if (ok(0)) b = 0;
+        while (a < b) {
+            const uint64_t mid = a + (b - a) / 2;
+            if (ok(mid)) b = mid;
+            else a = mid + 1;
+        }
+        thr[r - 1] = f64_from_bits(b);
+    }
+    return true;
+}
+
+} // namespace qd

@@ -211,6 +211,35 @@ typedef int (*FastSegmentFn)(Chain &c, void *user, int j, uint64_t u0, uint64_t 
 int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, bool samples_sink,
                    float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done);
 
+// ---------------------------------------------------------------- STFT kernels (qd_generic.cu, qd_stft.cu)
+enum { EPI_SPARK = 0, EPI_LEVELS = 1, EPI_TAKE = 2 };
+
+struct FftArgs {
+    const float2 *in;     // cf32 windows: window u starts at in + u * in_pitch
+    uint64_t in_pitch;
+    const uint8_t *raw;   // or raw capture bytes (decoded on load): window u starts at sample raw_first + u * in_pitch
+    int raw_fmt;
+    uint64_t raw_first;
+    uint64_t n_units;
+    const float2 *tw;     // w(W, j), j < W
+    const float *window;  // nullable (take_fft BlackmanHarris)
+    uint32_t W;
+    uint32_t team;        // threads cooperating on one window
+    int epi;
+    float mn, mx, distinction;
+    uint8_t *idx;         // SPARK [units][W]; LEVELS [units]
+    float *mag;           // SPARK nullable / TAKE [units][W]
+    int *panic_flag;
+    // glyph boundaries as thresholds on re^2 + im^2 in f64 (spark_thresholds): lets the index be found
+    // without the square root when magnitudes are not requested
+    int use_thr;
+    double thr[9];
+};
+// thr[c], c = 0..6: smallest s = fl64(re^2 + im^2) whose glyph index is >= c + 1; thr[7]: start of the
+// graph[7] panic zone; thr[8]: smallest s with norm >= max.  false when min/max make that ill-defined.
+bool spark_thresholds(float mn, float mx, double thr[9]);
+int launch_stft_fast(Chain &c, const FftArgs &fa, uint64_t units, bool *handled);
+
 int synth_fill(const qd_synth *p, int format, uint64_t first, uint64_t n, void *d_out, int device, cudaStream_t st);
 
 } // namespace qd

@@ -296,3 +296,35 @@ def test_fast_mode_full_size_config2_against_exact(Q):
     print(f"FAST vs EXACT over 2^30 samples: worst chunk rel err {worst:.3e}, mean {float(err.mean()):.3e}")
     assert worst <= 1e-5, worst
     assert not torch.equal(exact, fast)
+
+
+def test_shards_and_pointers_at_awkward_alignments(Q):
+    """Shard bases that are not multiples of 8 samples, host pointers at odd byte offsets, and a device
+    pointer that breaks the 16-byte rule (falls back to the general executor): same bits every time."""
+    import torch
+
+    n = 300_000
+    raw, _ = synth_raw(O.CS8, n)
+    st = [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)]
+    with kept_only():
+        want, _ = oracle_chain(raw, O.CS8, 20_000_000, st).write_mem()
+    for base in (3, 8 * 1237 + 5, 0x1000 * 8 * 3 + 1):
+        # the shard starts at raw sample `base`; chunks whose span lies inside it reproduce the unsharded bits
+        part = np.ascontiguousarray(raw[2 * base :])
+        first_chunk = -(-base // (0x1000 * 8))
+        g = gpu_chain(part, O.CS8, 20_000_000, st, base=base, total=n)
+        got, _ = g.write_mem(first_chunk=first_chunk, max_chunks=4)
+        assert_bit_equal(got, want[first_chunk * 0x1000 : first_chunk * 0x1000 + len(got)], f"host shard base {base}")
+        assert len(got) == 4 * 0x1000
+        # the same bytes at an odd device address: the fused kernel's bulk copies need absolute sample 0 on a
+        # 16-byte boundary, so this goes through the general executor
+        buf = torch.zeros(part.size + 64, dtype=torch.uint8, device="cuda")
+        off = 2 + 2 * (base % 7)  # sample-aligned, not 16-byte aligned
+        buf[off : off + part.size] = torch.from_numpy(part).cuda()
+        d = Q.Samples.from_device(buf.data_ptr() + off, part.size, Q.CS8, 20_000_000, base_sample=base, total_samples=n,
+                                  keep=(buf,)).shift(1_500_000).lowpass(1_000_000, 8, 40)
+        got, _ = d.write_mem(first_chunk=first_chunk, max_chunks=4)
+        assert_bit_equal(got, want[first_chunk * 0x1000 : first_chunk * 0x1000 + len(got)], f"device shard base {base}")
+        with pytest.raises(Q.QdError) as e:  # a device pointer in the middle of a sample is refused
+            Q.Samples.from_device(buf.data_ptr() + 1, part.size, Q.CS8, 20_000_000)
+        assert e.value.code == Q._lib.E_INVALID_ARG

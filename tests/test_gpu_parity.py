@@ -387,3 +387,68 @@ def test_device_resident_source_and_device_outputs(Q):
     with kept_only():
         widx, _ = oracle_chain(raw, O.CS8, 20_000_000, st).spark_fft(64, 64, (0.05, 2.0))
     assert np.array_equal(d_idx.cpu().numpy().reshape(rows, 64), widx)
+
+
+# ---------------------------------------------------------------- fast STFT kernel, every width
+@pytest.mark.parametrize("logw", range(0, 13))
+def test_stft_every_width_both_epilogues(Q, logw):
+    """fk_stft (qd_stft.cu): widths 1..4096, windows cut from raw bytes and from a filtered stream, glyph
+    index via the f64 thresholds (no magnitudes requested) and via hypot (magnitudes requested)."""
+    W = 1 << logw
+    S = max(1, W // 3)
+    n = max(20_000, 6 * W)
+    raw, _ = synth_raw(O.CS8, n)
+    rng = (0.3 * np.sqrt(W) / 8, 4.0 * np.sqrt(W))
+    for stages in ([], [("lowpass", 4_000_000, 2, 4)]):
+        o, g = oracle_chain(raw, O.CS8, 20_000_000, stages), gpu_chain(raw, O.CS8, 20_000_000, stages)
+        with kept_only():
+            widx, wmag = o.spark_fft(W, S, rng)
+        idx_only, _ = g.spark_fft(W, S, rng, want_mag=False)
+        idx, mag = g.spark_fft(W, S, rng, want_mag=True)
+        assert widx.shape[0] > 3
+        assert np.array_equal(idx_only, widx), f"threshold path W={W}: {(idx_only != widx).sum()} differ"
+        assert np.array_equal(idx, widx), f"hypot path W={W}"
+        assert_bit_equal(mag, wmag, f"magnitudes W={W}")
+        assert len(np.unique(widx)) >= 3  # the range really splits the bins into several glyphs
+        ref, _ = g.set_option("use_fast", 0).spark_fft(W, S, rng, want_mag=False)
+        assert np.array_equal(ref, widx)
+
+
+def test_stft_thresholds_on_special_values(Q):
+    # magnitudes exactly on glyph boundaries, zeros, denormals, huge values, inf and NaN (fft.rs:53-60)
+    def run(chain, W, S, rng_):
+        try:
+            idx, _ = chain.spark_fft(W, S, rng_)
+            return 0, idx
+        except (O.OracleError, Q.QdError) as e:
+            return e.code, None
+
+    # a range whose top glyph boundary does not reach graph[7] (the default 0.08:1 does: see below)
+    lo, hi = next((a, b) for a, b in [(0.08, 1.0), (0.1, 1.5), (0.05, 2.0), (0.2, 3.0)]
+                  if O.glyph_index(float(np.nextafter(np.float32(b), np.float32(0))), a, b) >= 0)
+    d = np.float32((np.float32(hi) - np.float32(lo)) / np.float32(7))
+    edges = [np.float32(lo) + np.float32(k) * d for k in range(8)]
+    vals = []
+    for e in edges:
+        vals += [np.nextafter(e, np.float32(0)), e, np.nextafter(e, np.float32(4))]
+    vals += [0.0, 1e-42, 1e-30, np.nextafter(np.float32(hi), np.float32(0)), hi, 3e38, np.inf, -np.inf, np.nan]
+    vals = np.array(vals, dtype=np.float32)
+    sig = np.zeros(2 * len(vals), dtype=np.complex64)
+    sig.real[0::2] = vals          # real part only
+    sig.imag[1::2] = vals          # imaginary part only
+    sig = np.concatenate([sig, np.array([3 + 4j, 0.06 + 0.08j, complex(np.inf, np.nan), complex(np.nan, 1)], dtype=np.complex64),
+                          np.zeros(2, dtype=np.complex64)])
+    raw = sig.view(np.uint8)
+    o = O.Samples.from_bytes(raw, O.CF32, 1000)
+    g = Q.Samples.from_bytes(raw, Q.CF32, 1000)
+    rc_o, widx = run(o, 1, 1, (lo, hi))                        # width 1: each magnitude is |sample|
+    rc_g, idx = run(g, 1, 1, (lo, hi))
+    assert rc_o == rc_g == 0
+    assert np.array_equal(idx, widx), (idx.ravel(), widx.ravel())
+    # the default range (which hits the reference's graph[7] panic just below 1.0), an inverted one, a tiny one
+    for rng_ in (None, (0.5, 0.2), (0.0, 1e-3)):
+        rc_o, widx = run(o, 2, 1, rng_)
+        rc_g, idx = run(g, 2, 1, rng_)
+        assert rc_o == rc_g, (rng_, rc_o, rc_g)
+        if rc_o == 0:
+            assert np.array_equal(idx, widx), rng_
