@@ -102,33 +102,81 @@ def make_oracle_synth(O, w):
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region (NVML, ~1 ms period, from a thread:
+    ctypes releases the GIL while the library call runs).  Falls back to nvidia-smi -lms when NVML is missing."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
+        self.samples = []  # (sm_mhz, reasons_mask)
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        self.mode = None
         self.proc = None
         self.lines = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
-            self.t.start()
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            pass
+        try:
+            q = ("index,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi"
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
         except OSError:
-            self.proc = None
+            self.mode = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.samples.append((float(sm), int(mask)))
+            except Exception:
+                break
+            time.sleep(0.001)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        if self.mode == "nvml":
+            self.stop_flag.set()
+            self.thread.join(timeout=1)
+            sm = sorted(x[0] for x in self.samples)
+            mask = 0
+            for _, m in self.samples:
+                mask |= m
+            reasons = sorted(name for bit, name in self.REASONS.items() if mask & bit)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
@@ -138,19 +186,19 @@ class ClockSampler:
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 7:
                 continue
             try:
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
             except ValueError:
                 continue
-            for name, val in zip(names, f[5:9]):
+            for name, val in zip(names, f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -371,6 +419,12 @@ def run_b200(args, w):
             peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
         # algorithmic bytes: input read once + final output written once (cf32 for write, u8 per bin for sparkfft)
         alg_bytes = n_in * pb + (produced * 8 if sk == 0 else n_units * unit_len)
+        traffic, traffic_src = None, None
+        tpath = ROOT / "profiles" / "traffic.json"
+        if tpath.exists():
+            ent = json.loads(tpath.read_text()).get(f"{args.workload}:{'fast' if precision == Q.FAST else 'exact'}:{per_gpu}")
+            if ent:
+                traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
         kern_avg_ms = kern_ms / max(1, args.steps)  # device ms per step of the dominant kernel (CUDA events around its launches)
         achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_avg_ms > 0 else None
         value = total_samples_step / (ms_dev * 1e-3) / 1e6
@@ -386,7 +440,8 @@ def run_b200(args, w):
             "clocks": clocks,
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "kernel": kern_name,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": kern_name,
                          "kernel_ms_per_step": kern_avg_ms, "algorithmic_bytes_per_step": alg_bytes,
                          "peak_source": peak_src},
         }
