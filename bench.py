@@ -425,6 +425,21 @@ def run_b200(args, w):
             ent = json.loads(tpath.read_text()).get(f"{args.workload}:{'fast' if precision == Q.FAST else 'exact'}:{per_gpu}")
             if ent:
                 traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+        # FP32 co-bound of the FIR: complex MACs per input sample, each one packed FFMA2 in FAST
+        # mode and two packed instructions (FMUL2 + FFMA2) in the reference's exact mul-then-add order; the FMA
+        # pipe retires 64 packed lanes per clock per SM
+        macs, rate_div = 0.0, 1
+        for st in w["stages"]:
+            if st[0] == "lowpass":
+                rate_div *= st[2]
+                macs += st[3] / rate_div
+        fir = None
+        if macs:
+            instr = macs * (1 if precision == Q.FAST else 2)
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_instr = torch.cuda.get_device_properties(dev).multi_processor_count * 64 * sm_mhz * 1e6
+            fir = {"complex_macs_per_sample": macs, "packed_instr_per_sample": instr,
+                   "ceiling_msamples_per_s": peak_instr / instr / 1e6}
         kern_avg_ms = kern_ms / max(1, args.steps)  # device ms per step of the dominant kernel (CUDA events around its launches)
         achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_avg_ms > 0 else None
         value = total_samples_step / (ms_dev * 1e-3) / 1e6
@@ -443,8 +458,10 @@ def run_b200(args, w):
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                          "kernel": kern_name,
                          "kernel_ms_per_step": kern_avg_ms, "algorithmic_bytes_per_step": alg_bytes,
-                         "peak_source": peak_src},
+                         "peak_source": peak_src, "fir_fp32_cobound": fir},
         }
+        if fir:
+            fir["frac_of_ceiling"] = (value / world) / fir["ceiling_msamples_per_s"]
         if exact_ms:
             line["exact_mode"] = {"value": total_samples_step / (exact_ms * 1e-3) / 1e6, "unit": "Msamples/s",
                                   "ms_per_step": exact_ms,

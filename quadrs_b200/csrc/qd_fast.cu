@@ -40,7 +40,7 @@ struct FirArgs {
     double ratio[kMaxLeadShifts];
     const double *sincos;
     SinCosK k;
-    uint32_t L, Q, Lrem; // L = (Q-1)*D + Lrem, 1 <= Lrem <= D
+    uint32_t L;          // filter length
     uint64_t off0;       // top-level (decimated) index of unit 0's first output
     uint64_t n_call;     // outputs per unit (the n of LowPass::read_at)
     uint64_t S;          // unit stride in top-level samples
@@ -110,6 +110,12 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                      smem_u32(dst)),
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// bulk prefetch of a byte range into L2 (no registers, no shared memory)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 // ---------------------------------------------------------------------------- exact integer decode
@@ -245,12 +251,19 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
             ph_g = cmul_fast(ph_g, make_float2(fmaf(-e, sf, cf), fmaf(e, cf, sf)));
         }
     }
+    // cf32 groups come from global memory (L2, after the bulk prefetch): keep the next group's loads in flight
+    uint4 nlo = make_uint4(0, 0, 0, 0), nhi = make_uint4(0, 0, 0, 0);
+    auto fetch = [&](uint32_t grp) {
+        nlo = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp);
+        nhi = make_uint4(0, 0, 0, 0);
+        if (static_cast<int>(4 * grp + 2) < n_have) nhi = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp + 1);
+    };
+    if (FMT == QD_FMT_CF32 && static_cast<uint32_t>(tid) < n_groups) fetch(tid);
     for (uint32_t grp = tid; grp < n_groups; grp += NT) {
         uint32_t w[8];
         if (FMT == QD_FMT_CF32) {
-            const uint4 lo = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp);
-            uint4 hi = make_uint4(0, 0, 0, 0);
-            if (static_cast<int>(4 * grp + 2) < n_have) hi = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp + 1);
+            const uint4 lo = nlo, hi = nhi;
+            if (grp + NT < n_groups) fetch(grp + NT);
             w[0] = lo.x, w[1] = lo.y, w[2] = lo.z, w[3] = lo.w, w[4] = hi.x, w[5] = hi.y, w[6] = hi.z, w[7] = hi.w;
         } else if (FMT == QD_FMT_CS16) {
             const uint4 v = *(reinterpret_cast<const uint4 *>(raw) + grp);
@@ -422,20 +435,23 @@ __global__ void __launch_bounds__(NT, 2) fk_fir(const __grid_constant__ FirArgs 
     __syncthreads();
 
     // raw byte range of a tile, widened to 16-byte boundaries for the bulk copy
-    auto issue = [&](const TileGeo &g, int buf) {
+    auto issue = [&](const TileGeo &g) {
         const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + a.L;
         const uint64_t n_dec = min(span, a.src_end - g.n_tile0);
         const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * pb;
         const uint8_t *abeg = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
         const uintptr_t gend = reinterpret_cast<uintptr_t>(gbeg + n_dec * pb);
         const uint32_t bytes = static_cast<uint32_t>(((gend + 15) & ~uintptr_t(15)) - reinterpret_cast<uintptr_t>(abeg));
-        (void)buf;
-        mbar_expect_tx(&mbar[0], bytes);
-        bulk_g2s(raw0, abeg, bytes, &mbar[0]);
+        if (staged) {
+            mbar_expect_tx(&mbar[0], bytes);
+            bulk_g2s(raw0, abeg, bytes, &mbar[0]);
+        } else {
+            bulk_prefetch_l2(abeg, bytes); // cf32: the decode stage reads global memory; make it an L2 hit
+        }
     };
 
     uint64_t it = 0;
-    if (staged && tid == 0 && blockIdx.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, blockIdx.x), 0);
+    if (tid == 0 && blockIdx.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, blockIdx.x));
 
     for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
         const TileGeo g = tile_geo<D, Gm::T_OUT>(a, tile);
@@ -468,7 +484,7 @@ __global__ void __launch_bounds__(NT, 2) fk_fir(const __grid_constant__ FirArgs 
         }
         __syncthreads();
         // the raw bytes are consumed: fetch the next tile's while this one is filtered
-        if (staged && tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x), 0);
+        if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x));
 
         // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
         if (static_cast<uint32_t>(R * tid) < g.cnt) {
@@ -633,8 +649,6 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     a.k = make_sincos_k();
     const uint32_t D = lp.D, R = static_cast<uint32_t>(lp.shape.R);
     a.L = lp.L;
-    a.Q = (a.L + D - 1) / D;
-    a.Lrem = a.L - (a.Q - 1) * D;
     a.off0 = off0;
     a.n_call = n_call;
     a.S = S;
@@ -702,8 +716,7 @@ static uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
 constexpr uint64_t kStreamCall = uint64_t(1) << 40; // "one read that never ends": no truncation inside a stream
 
 // see qd_internal.h
-int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, bool samples_sink,
-                   float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done)
+int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done)
 {
     *units_done = 0;
     const FastPlan f = fast_plan(c, unit_len, stride, n_units);
@@ -832,7 +845,6 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
         QD_CUDA(cudaEventRecord(c.ev_compute[j], c.stream)); // the raw staging buffer may be refilled
         if (on_segment) QD_TRY(on_segment(c, user, j, u0, nu, d_top, pitch));
     }
-    (void)samples_sink;
     *units_done = n_full;
     return QD_OK;
 }

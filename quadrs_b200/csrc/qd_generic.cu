@@ -861,8 +861,7 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
         float2 *direct = (sink.kind == SINK_SAMPLES && sink.space == QD_SPACE_DEVICE)
                              ? reinterpret_cast<float2 *>(sink.samples_out)
                              : nullptr;
-        QD_TRY(run_units_fast(c, off0, stride, n_units, unit_len, sink.kind == SINK_SAMPLES, direct, fast_segment_sink, &ctx,
-                              &done));
+        QD_TRY(run_units_fast(c, off0, stride, n_units, unit_len, direct, fast_segment_sink, &ctx, &done));
         used_pipeline = done > 0;
         produced = sink.kind == SINK_SAMPLES ? done * unit_len : done;
         if (used_pipeline) {

@@ -208,8 +208,7 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
 // d_top/pitch: unit u of the segment starts at d_top + u*pitch (pitch = unit_len for a [units][n] matrix,
 // = stride when the top stage was materialised as one contiguous stream).
 typedef int (*FastSegmentFn)(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, const float2 *d_top, uint64_t pitch);
-int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, bool samples_sink,
-                   float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done);
+int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done);
 
 // ---------------------------------------------------------------- STFT kernels (qd_generic.cu, qd_stft.cu)
 enum { EPI_SPARK = 0, EPI_LEVELS = 1, EPI_TAKE = 2 };
