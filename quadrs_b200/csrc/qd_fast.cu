@@ -415,7 +415,7 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
 }
 
 template <int D, int R, int NT, bool EXACT, int LS>
-__global__ void __launch_bounds__(NT, 2) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
+__global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
 {
     using Gm = FirGeom<D, R, NT>;
     constexpr int DR = Gm::DR;
@@ -535,8 +535,8 @@ static bool fir_shape(uint64_t D, FirShape *s)
     switch (D) {
     case 2: *s = {8, 128}; return true;
     case 4: *s = {8, 128}; return true;
-    case 8: *s = {4, 256}; return true;
-    case 16: *s = {4, 128}; return true;
+    case 8: *s = {4, 128}; return true;
+    case 16: *s = {2, 256}; return true;
     case 32: *s = {2, 128}; return true;
     }
     return false;
@@ -677,8 +677,8 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     switch (D) {
     case 2: return launch_fir_dr<2, 8, 128>(c, a, taps, exact);
     case 4: return launch_fir_dr<4, 8, 128>(c, a, taps, exact);
-    case 8: return launch_fir_dr<8, 4, 256>(c, a, taps, exact);
-    case 16: return launch_fir_dr<16, 4, 128>(c, a, taps, exact);
+    case 8: return launch_fir_dr<8, 4, 128>(c, a, taps, exact);
+    case 16: return launch_fir_dr<16, 2, 256>(c, a, taps, exact);
     case 32: return launch_fir_dr<32, 2, 128>(c, a, taps, exact);
     }
     return set_error(QD_E_INVALID_ARG, "internal: no fused FIR for decimate %u", D);
