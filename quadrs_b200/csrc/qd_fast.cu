@@ -153,11 +153,12 @@ __device__ __forceinline__ float2 decode_in_group(const uint32_t (&w)[8], int i,
 // ---------------------------------------------------------------------------- tile geometry
 constexpr int pitch_for(int G, int cols)
 {
-    // a half-warp storing 16 float2 must hit 16 distinct bank pairs: with G >= 16 consecutive lanes
-    // store to consecutive rows (odd pitch); with smaller G they alternate rows and columns
-    if (G >= 16) return cols | 1;
+    // elements are 16 bytes (a PAIR of consecutive samples): a quarter-warp storing 8 of them must hit 8
+    // distinct 16-byte bank groups.  With G >= 8 consecutive lanes store to consecutive rows (odd pitch);
+    // with G = 4 they cover 4 rows x 2 columns (pitch = 2 mod 8)
+    if (G >= 8) return cols | 1;
     int p = cols;
-    while (p % 16 != 16 / G) p++;
+    while (p % 8 != 8 / G) p++;
     return p;
 }
 
@@ -169,8 +170,8 @@ struct FirGeom {
     static constexpr int LOG_G = LOG_DR - 2;
     static constexpr int T_OUT = R * NT;
     static constexpr int COLS = NT + ((R - 1) * D + kMaxTapPairs + DR - 1) / DR + 1;
-    static constexpr int PITCH = pitch_for(G, COLS);
-    static constexpr size_t X_BYTES = static_cast<size_t>(DR) * PITCH * sizeof(float2);
+    static constexpr int PITCH = pitch_for(G, COLS); // float4 (sample pairs) per row; there are DR/2 rows
+    static constexpr size_t X_BYTES = static_cast<size_t>(DR / 2) * PITCH * sizeof(float4);
     static_assert(DR == 16 || DR == 32 || DR == 64, "polyphase period must be 16, 32 or 64");
 };
 
@@ -206,11 +207,12 @@ __device__ __forceinline__ TileGeo tile_geo(const FirArgs &a, uint64_t tile)
 }
 
 // ---------------------------------------------------------------------------- decode + mix stage
-// Local sample l lives at X[prow(l mod DR)][l div DR], prow(r) = (r & 3) * G + (r >> 2).  A lane
-// handles one 16-byte-aligned group of 4 raw samples; its neighbours handle the next groups, so for a
-// fixed position in the group the half-warp writes to consecutive physical rows: conflict-free.
-// ALIGNED: the tile's first sample sits on a group boundary (lead % 4 == 0), the common case, and the
-// four stores of a group are one base address plus compile-time offsets.
+// Samples are kept in PAIRS (16 bytes): pair P = l / 2 lives at X[prow(P mod DR/2)][P div DR/2] with
+// prow(r) = (r & 1) * G + (r >> 1), G = DR/4.  A lane handles one 16-byte-aligned group of 4 raw samples
+// (two pairs); its neighbours handle the next groups, so for a fixed pair of the group a quarter-warp
+// writes to consecutive physical rows: conflict-free 128-bit stores.  The FIR reads one row at consecutive
+// columns with 128-bit loads.  ALIGNED: the tile's first sample sits on a group boundary (lead % 4 == 0),
+// the common case, and the two stores of a group are one base address plus compile-time offsets.
 // FAST mode complex multiply: contraction allowed
 __device__ __forceinline__ float2 cmul_fast(float2 a, float2 b)
 {
@@ -304,39 +306,46 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
                 for (int s = 1; s < n_shift; s++) v[i] = mix_exact(v[i], nd, a.ratio[s], a);
             }
         }
+        float4 *X4 = reinterpret_cast<float4 *>(X);
         if (ALIGNED) {
             const uint32_t gc = grp - (lead >> 2); // local group index (wraps for the skipped lead groups)
-            float2 *xb = X + (gc & (Gm::G - 1)) * Gm::PITCH + (gc >> Gm::LOG_G);
+            float4 *xb = X4 + (gc & (Gm::G - 1)) * Gm::PITCH + (gc >> Gm::LOG_G);
             if (interior) {
-#pragma unroll
-                for (int i = 0; i < 4; i++) xb[i * Gm::G * Gm::PITCH] = v[i];
+                xb[0] = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+                xb[Gm::G * Gm::PITCH] = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
-                    if (g4 + i >= static_cast<int>(lead) && g4 + i < n_have) xb[i * Gm::G * Gm::PITCH] = v[i];
+                    if (g4 + i >= static_cast<int>(lead) && g4 + i < n_have)
+                        reinterpret_cast<float2 *>(xb + (i >> 1) * Gm::G * Gm::PITCH)[i & 1] = v[i];
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int l = g4 + i - static_cast<int>(lead);
                 if (l < 0 || l >= static_cast<int>(n_dec)) continue;
-                const uint32_t r = static_cast<uint32_t>(l) & (Gm::DR - 1);
-                X[((r & 3) * Gm::G + (r >> 2)) * Gm::PITCH + (static_cast<uint32_t>(l) >> Gm::LOG_DR)] = v[i];
+                const uint32_t pr = (static_cast<uint32_t>(l) >> 1) & (Gm::DR / 2 - 1);
+                float4 *el = X4 + ((pr & 1) * Gm::G + (pr >> 1)) * Gm::PITCH + (static_cast<uint32_t>(l) >> Gm::LOG_DR);
+                reinterpret_cast<float2 *>(el)[l & 1] = v[i];
             }
         }
     }
 }
 
 // ---------------------------------------------------------------------------- FIR stage
-// Block b of a thread = its local samples s = b*D .. b*D+D-1: row (b mod R)*D + p, column tid + b div R.
+// Block b of a thread = its local samples s = b*D .. b*D+D-1: pair rows (b mod R)*D/2 + p/2, column tid + b div R.
 template <int D, int R, int NT>
 __device__ __forceinline__ void load_block(const float2 *__restrict__ xcol, int rb, float2 (&v)[D])
 {
     using Gm = FirGeom<D, R, NT>;
+    static_assert(D % 2 == 0, "pairs of samples");
+    const float4 *xc4 = reinterpret_cast<const float4 *>(xcol);
 #pragma unroll
-    for (int p = 0; p < D; p++) {
-        const int r = rb * D + p;
-        v[p] = xcol[((r & 3) * Gm::G + (r >> 2)) * Gm::PITCH];
+    for (int p = 0; p < D; p += 2) {
+        const int r = rb * (D / 2) + p / 2;
+        const float4 q = xc4[((r & 1) * Gm::G + (r >> 1)) * Gm::PITCH];
+        v[p] = make_float2(q.x, q.y);
+        v[p + 1] = make_float2(q.z, q.w);
     }
 }
 
@@ -348,7 +357,7 @@ __device__ __forceinline__ void general_block(const float2 *__restrict__ X, int 
     const int plim = s_end - b * D;
     if (plim <= 0) return;
     float2 v[D];
-    load_block<D, R, NT>(X + tid + b / R, b & (R - 1), v);
+    load_block<D, R, NT>(X + 2 * (tid + b / R), b & (R - 1), v);
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int qb = b - r; // tap block of output r at this step
@@ -375,7 +384,7 @@ __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         float2 v[D];
-        load_block<D, R, NT>(X + tid + b / R, b % R, v);
+        load_block<D, R, NT>(X + 2 * (tid + b / R), b % R, v);
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int qb = b - r;
@@ -402,7 +411,7 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
 #pragma unroll
         for (int k = 0; k < R; k++) {
             float2 v[D];
-            load_block<D, R, NT>(X + tid + (b + k) / R, (R - 1 + k) % R, v);
+            load_block<D, R, NT>(X + 2 * (tid + (b + k) / R), (R - 1 + k) % R, v);
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const float2 *tp = taps.t + (b + k - r) * D;
