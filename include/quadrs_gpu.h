@@ -162,7 +162,8 @@ int qd_freq_levels(qd_chain *c, size_t width, uint64_t stride, size_t levels, ui
                    uint8_t *vals, int space, uint64_t *total);
 
 /* take_fft (ffts.rs:18-85): out[output_len * width] fftshifted magnitudes; windowing 0 Rectangular,
- * 1 BlackmanHarris (ffts.rs:12-16,110-119). */
+ * 1 BlackmanHarris (ffts.rs:12-16,110-119).  Any width 1..16384, as FftPlanner allows: powers of two run
+ * the radix-4 FFT, other widths a direct DFT with f64 accumulation. */
 int qd_take_fft(qd_chain *c, int has_slice, uint64_t start, uint64_t end, size_t width, int windowing,
                 size_t output_len, float *out, int space);
 

@@ -629,6 +629,45 @@ typedef struct {
 
 static int is_pow2(size_t n) { return n && !(n & (n - 1)); }
 
+/* FftPlanner::plan_fft_forward (ffts.rs:25) accepts ANY length; rustfft's mixed-radix / Rader / Bluestein
+ * code is not in the reference tree.  Our definition for a length that is not a power of two is the direct
+ * DFT  X[k] = sum_j x[j] * w(N, (j*k) mod N)  with the f32 twiddles above, products and the running sum in
+ * f64 (an f32 x f32 product is exact in f64, so every term is rounded once, on addition), ascending j,
+ * rounded to f32 at the end.  The GPU kernel gk_dft evaluates exactly this. */
+static void plan_init_any(fft_plan *p, size_t n)
+{
+    if (n == 0) qo_panic(QO_E_FFT_WIDTH, "FFT length 0");
+    p->n = n;
+    p->T = xcalloc(n, sizeof(qo_cf32));
+    p->scratch = xcalloc(n, sizeof(qo_cf32));
+    fft_twiddles(n, p->T);
+}
+
+static void plan_process_any(fft_plan *p, qo_cf32 *buf)
+{
+    if (is_pow2(p->n)) {
+        fft_rec(buf, 1, p->n, p->scratch, p->T, p->n);
+    } else {
+        const size_t n = p->n;
+        for (size_t k = 0; k < n; k++) {
+            double re = 0.0, im = 0.0;
+            size_t m = 0; /* (j*k) mod n */
+            for (size_t j = 0; j < n; j++) {
+                const double xr = buf[j].re, xi = buf[j].im, wr = p->T[m].re, wi = p->T[m].im;
+                re = re + xr * wr;
+                re = re - xi * wi;
+                im = im + xr * wi;
+                im = im + xi * wr;
+                m += k;
+                if (m >= n) m -= n;
+            }
+            p->scratch[k].re = (float)re;
+            p->scratch[k].im = (float)im;
+        }
+    }
+    memcpy(buf, p->scratch, p->n * sizeof(qo_cf32));
+}
+
 static void plan_init(fft_plan *p, size_t n)
 {
     if (!is_pow2(n)) qo_panic(QO_E_FFT_WIDTH, "Radix4 algorithm requires a power-of-two input size. Got %zu", n);
@@ -854,14 +893,13 @@ void qo_blackman_harris(size_t n, float *out)
     }
 }
 
-/* take_fft, ffts.rs:18-85.  Deviation: FftPlanner accepts any width; this
- * restatement (and the GPU path) accept powers of two only. */
+/* take_fft, ffts.rs:18-85 (any width, as FftPlanner allows) */
 int qo_take_fft(const qo_samples *s, int has_slice, uint64_t start, uint64_t end, size_t width, int blackman_harris,
                 size_t output_len, float *out)
 {
     QO_ENTER();
     fft_plan plan;
-    plan_init(&plan, width);
+    plan_init_any(&plan, width); /* FftPlanner: any width */
     uint64_t len = s_len(s);
     uint64_t start_sample = has_slice ? start : 0;
     uint64_t end_sample = has_slice ? end : len - (uint64_t)width;
@@ -902,7 +940,7 @@ int qo_take_fft(const qo_samples *s, int has_slice, uint64_t start, uint64_t end
                 cbuf[j].re = cbuf[j].re * window[j];
                 cbuf[j].im = cbuf[j].im * window[j];
             }
-        plan_process(&plan, cbuf);
+        plan_process_any(&plan, cbuf);
         for (size_t b = 0; b < width; b++) {
             size_t src = b < width - width / 2 ? b + width / 2 : b - (width - width / 2);
             out[i * width + b] = hypotf(cbuf[src].re, cbuf[src].im);

@@ -482,8 +482,8 @@ int qd_take_fft(qd_chain *c, int has_slice, uint64_t start, uint64_t end, size_t
                 size_t output_len, float *out, int space)
 {
     if (!c) return set_error(QD_E_INVALID_ARG, "chain is null");
-    // FftPlanner accepts any length (ffts.rs:25); this library supports powers of two only.
-    if (!is_pow2(width)) return set_error(QD_E_FFT_WIDTH, "take_fft width must be a power of two here. Got %zu", width);
+    // FftPlanner accepts any length (ffts.rs:25): powers of two run the radix-4 FFT, others a direct DFT
+    if (width == 0 || width > 16384) return set_error(QD_E_FFT_WIDTH, "take_fft width %zu unsupported (1..16384)", width);
     std::lock_guard<std::mutex> lk(c->mu);
     uint64_t len = 0;
     QD_TRY(chain_len(*c, &len));

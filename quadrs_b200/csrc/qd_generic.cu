@@ -216,6 +216,46 @@ __global__ void gk_fft(FftArgs a)
     }
 }
 
+// ---- any width that is not a power of two (take_fft only: FftPlanner accepts any length, ffts.rs:25) ----
+// Direct DFT  X[k] = sum_j x[j] * w(W, (j*k) mod W), products and running sum in f64 (each f32 x f32 product
+// is exact in f64, so every term costs one rounding), ascending j, rounded to f32 at the end -- the same
+// definition as oracle/quadrs_oracle.c plan_process_any, hence bit-identical.  One CTA per window.
+__global__ void gk_dft(FftArgs a)
+{
+    extern __shared__ float2 dft_smem[];
+    const uint32_t W = a.W;
+    const uint64_t u = blockIdx.x;
+    for (uint32_t n = threadIdx.x; n < W; n += blockDim.x) {
+        float2 v = a.in[u * a.in_pitch + n];
+        if (a.window) {
+            const float w = a.window[n];
+            v = make_float2(__fmul_rn(v.x, w), __fmul_rn(v.y, w));
+        }
+        dft_smem[n] = v;
+    }
+    __syncthreads();
+    const uint32_t half = W / 2;
+    for (uint32_t k = threadIdx.x; k < W; k += blockDim.x) {
+        double re = 0.0, im = 0.0;
+        uint32_t m = 0; // (j * k) mod W
+        for (uint32_t j = 0; j < W; j++) {
+            const float2 x = dft_smem[j];
+            const float2 w = __ldg(a.tw + m);
+            const double xr = x.x, xi = x.y, wr = w.x, wi = w.y;
+            re = fma(xr, wr, re); // exact product, one rounding: re + xr*wr
+            re = fma(-xi, wi, re);
+            im = fma(xr, wi, im);
+            im = fma(xi, wr, im);
+            m += k;
+            if (m >= W) m -= W;
+        }
+        const float norm = hypot_exact(static_cast<float>(re), static_cast<float>(im));
+        // iter().skip(w/2).chain(iter().take(w/2)), ffts.rs:72-76: bin k lands at display column b
+        const uint32_t b = k >= half ? k - half : k + (W - half);
+        a.mag[static_cast<size_t>(u) * W + b] = norm;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // host orchestration
 // ------------------------------------------------------------------------------------------
@@ -544,6 +584,17 @@ int launch_fft(Chain &c, FftArgs &fa, uint64_t units)
 {
     if (units == 0) return QD_OK;
     const uint32_t W = fa.W;
+    if (W & (W - 1)) { // not a power of two: direct DFT (take_fft only)
+        if (fa.epi != EPI_TAKE || fa.raw) return set_error(QD_E_FFT_WIDTH, "internal: width %u needs the take_fft sink", W);
+        fa.n_units = units;
+        const size_t smem = static_cast<size_t>(W) * sizeof(float2);
+        if (smem > 48 * 1024)
+            QD_CUDA(cudaFuncSetAttribute(gk_dft, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        if (units > 0x7fffffffull) return set_error(QD_E_INVALID_ARG, "too many windows in one launch");
+        gk_dft<<<static_cast<unsigned>(units), 256, smem, c.stream>>>(fa);
+        QD_LAUNCHED();
+        return QD_OK;
+    }
     if (c.use_fast && fa.epi == EPI_SPARK && W <= 4096 && !fa.window) {
         bool handled = false;
         QD_TRY(launch_stft_fast(c, fa, units, &handled));

@@ -318,7 +318,8 @@ def test_freq_levels_matches_oracle(Q):
     assert e.value.code == O.E_LEVELS
 
 
-@pytest.mark.parametrize("W,bh", [(64, False), (256, True), (4096, True), (4, False)])
+@pytest.mark.parametrize("W,bh", [(64, False), (256, True), (4096, True), (4, False), (12, True), (100, False), (513, True),
+                                  (1000, False)])  # any width: FftPlanner takes them all (ffts.rs:25)
 def test_take_fft_matches_oracle(Q, W, bh):
     raw, _ = synth_raw(O.CS8, 80_000)
     st = [("shift", 1_000_000), ("lowpass", 2_000_000, 4, 24)]
