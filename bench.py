@@ -472,7 +472,7 @@ def run_b200(args, w):
             line["e2e"] = {"value": total_samples_step / (ms_e2e_max * 1e-3) / 1e6, "unit": "Msamples/s",
                            "h2d_bytes_per_step": n_in * pb, "d2h_bytes_per_step": out_bytes,
                            "ms_per_step": ms_e2e_max, "same_as_device_path": e2e["same_as_device_path"]}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
             line["cpu_baseline"] = cpu_baseline(w, d_in, plan, pb)
         print(json.dumps(line), flush=True)
     if world > 1:
