@@ -129,7 +129,8 @@ __device__ __forceinline__ float2 div_exact2(float2 x, float den, float c)
 }
 
 // One sample of a 4-sample group held in w[] (FMT is compile time here)
-template <int FMT>
+// SCALED = false (FAST mode, cs8): the integer value itself; the kernel's taps carry the 1/127
+template <int FMT, bool SCALED = true>
 __device__ __forceinline__ float2 decode_in_group(const uint32_t (&w)[8], int i, float2 one)
 {
     if (FMT == QD_FMT_CF32) return make_float2(__uint_as_float(w[2 * i]), __uint_as_float(w[2 * i + 1])); // bit copy
@@ -137,6 +138,7 @@ __device__ __forceinline__ float2 decode_in_group(const uint32_t (&w)[8], int i,
         const uint32_t h = w[i >> 1] >> ((i & 1) * 16);
         const float x = static_cast<float>(static_cast<int>(static_cast<signed char>(h & 0xff)));
         const float y = static_cast<float>(static_cast<int>(static_cast<signed char>((h >> 8) & 0xff)));
+        if (!SCALED) return make_float2(x, y);
         return div_exact2(make_float2(x, y), 127.0f, 1.0f / 127.0f);
     }
     if (FMT == QD_FMT_CU8) { // lib.rs:252: x/255 - 127.5 (the subtraction as q*1 + (-127.5), one rounding)
@@ -180,6 +182,7 @@ struct TileGeo {
     uint64_t out0;    // index into out[]
     uint64_t f0;      // flat output index of the tile's first output (contiguous mode)
     uint64_t unit;    // non-contiguous mode
+    uint64_t u0;      // contiguous mode: unit that holds the tile's first output
     uint32_t cnt;     // outputs in this tile
 };
 
@@ -194,6 +197,7 @@ __device__ __forceinline__ TileGeo tile_geo(const FirArgs &a, uint64_t tile)
         g.cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(T_OUT), total - g.f0));
         g.out0 = g.f0;
         g.unit = 0;
+        g.u0 = g.f0 / a.n_call;
         g.n_tile0 = (a.off0 + g.f0) * D + i0;
     } else {
         g.unit = tile / a.tiles_per_unit;
@@ -201,6 +205,7 @@ __device__ __forceinline__ TileGeo tile_geo(const FirArgs &a, uint64_t tile)
         g.cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(T_OUT), a.n_call - k0));
         g.out0 = g.unit * a.n_call + k0;
         g.f0 = 0;
+        g.u0 = 0;
         g.n_tile0 = (a.off0 + g.unit * a.S + k0) * D + i0;
     }
     return g;
@@ -278,7 +283,7 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
         const bool interior = g4 >= static_cast<int>(lead) && g4 + 3 < n_have;
         float2 v[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) v[i] = decode_in_group<FMT>(w, i, one);
+        for (int i = 0; i < 4; i++) v[i] = decode_in_group<FMT, !FASTMIX>(w, i, one);
         if (FASTMIX) {
             if (n_shift) {
                 // the reference's phase is fl64(n*ratio) (shift.rs:49): its rounding error against the exact
@@ -500,8 +505,18 @@ __global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(co
             // the unit's raw buffer ends at (unit_top0 + n_call)*D + L: later samples do not exist for
             // this read (filter.rs:68-71) and the ascending tap loop stops there
             uint64_t unit_top0;
-            if (a.contiguous) unit_top0 = a.off0 + ((g.f0 + static_cast<uint64_t>(R * tid)) / a.n_call) * a.n_call;
-            else unit_top0 = a.off0 + g.unit * a.S;
+            if (a.contiguous) {
+                // one division per tile (g.u0 = f0 / n_call); a thread's outputs start `rel` past that unit
+                uint64_t rel = g.f0 - g.u0 * a.n_call + static_cast<uint64_t>(R * tid);
+                uint64_t un = g.u0;
+                while (rel >= a.n_call) { // the tile runs over one or more unit boundaries
+                    rel -= a.n_call;
+                    un++;
+                }
+                unit_top0 = a.off0 + un * a.n_call;
+            } else {
+                unit_top0 = a.off0 + g.unit * a.S;
+            }
             const uint64_t raw_end = (unit_top0 + a.n_call) * D + a.L;
             const int64_t s_lim = static_cast<int64_t>(raw_end - g.n_tile0) - static_cast<int64_t>(tid) * DR;
             const int L = LS > 0 ? LS : static_cast<int>(a.L);
@@ -681,8 +696,10 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     }
     FirTaps taps;
     memset(&taps, 0, sizeof taps);
-    for (uint32_t j = 0; j < a.L; j++) taps.t[j] = make_float2(st.taps[j], st.taps[j]);
     const bool exact = c.precision == QD_PRECISION_EXACT;
+    // FAST mode leaves cs8 samples as integers in the kernel and carries the 1/127 of lib.rs:251 in the taps
+    const float scale = (!exact && fmt == QD_FMT_CS8) ? 1.0f / 127.0f : 1.0f;
+    for (uint32_t j = 0; j < a.L; j++) taps.t[j] = make_float2(st.taps[j] * scale, st.taps[j] * scale);
     switch (D) {
     case 2: return launch_fir_dr<2, 8, 128>(c, a, taps, exact);
     case 4: return launch_fir_dr<4, 8, 128>(c, a, taps, exact);
