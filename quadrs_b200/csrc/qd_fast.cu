@@ -164,14 +164,14 @@ constexpr int pitch_for(int G, int cols)
     return p;
 }
 
-template <int D, int R, int NT>
+template <int D, int R, int NT, int LMAX = kMaxTapPairs>
 struct FirGeom {
     static constexpr int DR = D * R; // polyphase period
     static constexpr int G = DR / 4; // physical rows are grouped by (row & 3)
     static constexpr int LOG_DR = (DR == 16) ? 4 : (DR == 32) ? 5 : 6;
     static constexpr int LOG_G = LOG_DR - 2;
     static constexpr int T_OUT = R * NT;
-    static constexpr int COLS = NT + ((R - 1) * D + kMaxTapPairs + DR - 1) / DR + 1;
+    static constexpr int COLS = NT + ((R - 1) * D + LMAX + DR - 1) / DR + 1; // LMAX: longest filter this layout holds
     static constexpr int PITCH = pitch_for(G, COLS); // float4 (sample pairs) per row; there are DR/2 rows
     static constexpr size_t X_BYTES = static_cast<size_t>(DR / 2) * PITCH * sizeof(float4);
     static_assert(DR == 16 || DR == 32 || DR == 64, "polyphase period must be 16, 32 or 64");
@@ -231,11 +231,11 @@ __device__ __forceinline__ float2 mix_exact(float2 v, double nd, double ratio, c
     return cmul_exact(v, make_float2(static_cast<float>(c), static_cast<float>(sn)));
 }
 
-template <int FMT, int D, int R, int NT, bool ALIGNED, bool FASTMIX>
+template <int FMT, int D, int R, int NT, int LMAX, bool ALIGNED, bool FASTMIX>
 __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
                                             uint64_t n_tile0, float2 *__restrict__ X, int tid)
 {
-    using Gm = FirGeom<D, R, NT>;
+    using Gm = FirGeom<D, R, NT, LMAX>;
     const int n_have = static_cast<int>(n_dec + lead);
     const uint32_t n_groups = static_cast<uint32_t>(n_have + 3) / 4;
     // absolute index of raw group 0, sample 0, as an exact f64 (indices stay far below 2^53)
@@ -339,10 +339,10 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
 
 // ---------------------------------------------------------------------------- FIR stage
 // Block b of a thread = its local samples s = b*D .. b*D+D-1: pair rows (b mod R)*D/2 + p/2, column tid + b div R.
-template <int D, int R, int NT>
+template <int D, int R, int NT, int LMAX>
 __device__ __forceinline__ void load_block(const float2 *__restrict__ xcol, int rb, float2 (&v)[D])
 {
-    using Gm = FirGeom<D, R, NT>;
+    using Gm = FirGeom<D, R, NT, LMAX>;
     static_assert(D % 2 == 0, "pairs of samples");
     const float4 *xc4 = reinterpret_cast<const float4 *>(xcol);
 #pragma unroll
@@ -355,14 +355,14 @@ __device__ __forceinline__ void load_block(const float2 *__restrict__ xcol, int 
 }
 
 // every check at run time: prologue / epilogue blocks, partial tap blocks, truncated reads
-template <int D, int R, int NT, bool EXACT>
+template <int D, int R, int NT, int LMAX, bool EXACT>
 __device__ __forceinline__ void general_block(const float2 *__restrict__ X, int tid, int b, int s_end, int Q, int Lrem,
                                               const FirTaps &taps, float2 one, float2 (&acc)[R])
 {
     const int plim = s_end - b * D;
     if (plim <= 0) return;
     float2 v[D];
-    load_block<D, R, NT>(X + 2 * (tid + b / R), b & (R - 1), v);
+    load_block<D, R, NT, LMAX>(X + 2 * (tid + b / R), b & (R - 1), v);
 #pragma unroll
     for (int r = 0; r < R; r++) {
         const int qb = b - r; // tap block of output r at this step
@@ -381,7 +381,7 @@ __device__ __forceinline__ void general_block(const float2 *__restrict__ X, int 
 }
 
 // LS > 0: the filter length is a compile-time constant and the whole tap schedule unrolls
-template <int D, int R, int NT, bool EXACT, int LS>
+template <int D, int R, int NT, int LMAX, bool EXACT, int LS>
 __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid, const FirTaps &taps, float2 one,
                                            float2 (&acc)[R])
 {
@@ -389,7 +389,7 @@ __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid
 #pragma unroll
     for (int b = 0; b < NB; b++) {
         float2 v[D];
-        load_block<D, R, NT>(X + 2 * (tid + b / R), b % R, v);
+        load_block<D, R, NT, LMAX>(X + 2 * (tid + b / R), b % R, v);
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const int qb = b - r;
@@ -401,7 +401,7 @@ __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid
     }
 }
 
-template <int D, int R, int NT, bool EXACT>
+template <int D, int R, int NT, int LMAX, bool EXACT>
 __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int tid, int Q, int Lrem, int s_end,
                                             const FirTaps &taps, float2 one, float2 (&acc)[R])
 {
@@ -410,13 +410,13 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
     const int NB = R - 1 + Q;
     const int full = min(Q - 1, s_end / D); // blocks below this are complete and carry full tap blocks
     int b = 0;
-    for (; b < min(R - 1, NB); ++b) general_block<D, R, NT, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
+    for (; b < min(R - 1, NB); ++b) general_block<D, R, NT, LMAX, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
     // steady state: blocks R-1 <= b < Q-1 feed every output with a full tap block
     for (; b + R <= full; b += R) {
 #pragma unroll
         for (int k = 0; k < R; k++) {
             float2 v[D];
-            load_block<D, R, NT>(X + 2 * (tid + (b + k) / R), (R - 1 + k) % R, v);
+            load_block<D, R, NT, LMAX>(X + 2 * (tid + (b + k) / R), (R - 1 + k) % R, v);
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 const float2 *tp = taps.t + (b + k - r) * D;
@@ -425,13 +425,14 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
             }
         }
     }
-    for (; b < NB; ++b) general_block<D, R, NT, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
+    for (; b < NB; ++b) general_block<D, R, NT, LMAX, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
 }
 
 template <int D, int R, int NT, bool EXACT, int LS>
 __global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
 {
-    using Gm = FirGeom<D, R, NT>;
+    constexpr int LMAX = LS > 0 ? LS : kMaxTapPairs;
+    using Gm = FirGeom<D, R, NT, LMAX>;
     constexpr int DR = Gm::DR;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
@@ -482,17 +483,17 @@ __global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(co
                                         : reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
             if ((lead & 3) == 0) {
                 switch (a.fmt) {
-                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                default: decode_tile<QD_FMT_CF32, D, R, NT, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                default: decode_tile<QD_FMT_CF32, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
                 }
             } else {
                 switch (a.fmt) {
-                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                default: decode_tile<QD_FMT_CF32, D, R, NT, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                default: decode_tile<QD_FMT_CF32, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
                 }
             }
         }
@@ -529,10 +530,10 @@ __global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(co
             for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f); // Complex::zero(), filter.rs:112
 
             if (LS > 0 && s_lim >= s_total) {
-                fir_static<D, R, NT, EXACT, (LS > 0 ? LS : 1)>(X, tid, taps, one, acc);
+                fir_static<D, R, NT, LMAX, EXACT, (LS > 0 ? LS : 1)>(X, tid, taps, one, acc);
             } else { // also the tail of a read: outputs whose taps run past the end of the unit's raw buffer
                 const int s_end = static_cast<int>(min(static_cast<int64_t>(s_total), s_lim));
-                fir_dynamic<D, R, NT, EXACT>(X, tid, Q, Lrem, s_end, taps, one, acc);
+                fir_dynamic<D, R, NT, LMAX, EXACT>(X, tid, Q, Lrem, s_end, taps, one, acc);
             }
             float2 *o = a.out + g.out0 + static_cast<uint64_t>(R * tid);
             if (R % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
@@ -569,7 +570,7 @@ static bool fir_shape(uint64_t D, FirShape *s)
 template <int D, int R, int NT, bool EXACT, int LS>
 static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
 {
-    using Gm = FirGeom<D, R, NT>;
+    using Gm = FirGeom<D, R, NT, (LS > 0 ? LS : kMaxTapPairs)>;
     const size_t smem = 16 + Gm::X_BYTES + static_cast<size_t>(a.raw_cap);
     if (smem > 227 * 1024) return set_error(QD_E_INVALID_ARG, "internal: fused FIR tile needs %zu bytes of shared memory", smem);
     const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
