@@ -55,7 +55,22 @@ struct FirArgs {
     // FAST mode NCO: all leading shifts merged into one rotation of ratio_sum per sample
     float2 rot[4];    // e^{i k ratio_sum}, k = 0..3 (k = 0 unused)
     float2 rot_step;  // e^{i 4*NT ratio_sum}: from one group of a thread to its next
+    // lean cs8 path (one shift): |ratio[0]| = rmant * 2^rexp exactly, rsign = +-1 (0: ratio is zero)
+    uint64_t rmant;
+    int rexp;
+    int rsign;
 };
+
+// Per-tile phase state of the lean FAST decode, computed by one thread while the previous tile is filtered
+struct LeanPhase {
+    double ac, as;  // e^{i n_tile0 ratio} with the product taken exactly
+    uint64_t m64k;  // (rmant << (64 - k)) mod 2^64: n * m64k mod 2^64 = the k discarded bits of n*rmant, left aligned
+    uint32_t mk32;  // its high word: the per-sample increment of the 32-bit fraction
+    float esc;      // rsign * 2^(rexp + k - 32): fraction -> radians
+    int ok;         // the tile lies inside one binade of n*ratio (k is constant)
+    int pad;
+};
+constexpr int kSmemHeader = 64; // two mbarriers + LeanPhase
 
 // ---------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -75,6 +90,16 @@ __device__ __forceinline__ float2 mul2(float2 a, float2 b)
     float2 d;
     asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
         "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
         : "=f"(d.x), "=f"(d.y)
         : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return d;
@@ -337,6 +362,105 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
     }
 }
 
+// ---------------------------------------------------------------------------- lean FAST decode (cs8, <= 1 shift)
+// The common FAST case gets its own loop.  Decode: a byte b = x + 128 dropped into the mantissa of 2^23 is
+// the float 2^23 + b, and subtracting 2^23 + 128 leaves x exactly (two PRMT and one packed add per sample, no
+// integer->float conversion).  Phase: thread t's first group starts 4t samples into the tile, so its phasor
+// is (tile anchor) * e^{i 4t ratio}; the anchor is evaluated in f64 once per tile by one thread, the second
+// factor once per kernel.  The reference's phase is fl64(n * ratio) (shift.rs:49), off the exact product by
+// the k bits the multiply rounds away.  Those bits are n * rmant mod 2^k: kept left-aligned in a 64-bit
+// integer they advance by one wrapping add per group, and their top word read as a signed fraction of an
+// ulp is the rounding error (ties excepted: they round to even, here always up).
+__device__ __forceinline__ void lean_phase(const FirArgs &a, uint64_t n0, uint32_t span, LeanPhase *ph)
+{
+    const double nd = __ull2double_rn(n0), r = a.ratio[0];
+    const double p = __dmul_rn(nd, r);
+    const double e = fma(nd, r, -p); // exact product minus the rounded one
+    double c, s;
+    sincos_f64k(p, a.sincos, a.k, c, s);
+    ph->ac = fma(-e, s, c);
+    ph->as = fma(e, c, s);
+    const uint64_t M = a.rmant;
+    auto bitlen = [&](uint64_t n) {
+        const uint64_t hi = __umul64hi(n, M), lo = n * M;
+        return hi ? 128 - __clzll(static_cast<long long>(hi)) : 64 - __clzll(static_cast<long long>(lo));
+    };
+    const int b0 = bitlen(n0), b1 = bitlen(n0 + span);
+    const int k = b0 - 53; // bits rounded away (<= 64 since rmant < 2^53)
+    const int ee = a.rexp + k - 32;
+    uint64_t m64k = 0;
+    float esc = 0.0f;
+    if (k >= 1 && a.rsign != 0) {
+        m64k = k >= 64 ? M : (M << (64 - k));
+        if (ee >= -126 && ee <= 127) esc = __int_as_float((127 + ee) << 23) * static_cast<float>(a.rsign);
+    }
+    ph->m64k = m64k;
+    ph->mk32 = static_cast<uint32_t>(m64k >> 32);
+    ph->esc = esc;
+    ph->ok = (b0 == b1) ? 1 : 0;
+}
+
+template <int D, int R, int NT, int LMAX, bool MIX>
+__device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
+                                                 uint64_t n_tile0, const LeanPhase *lp, const double2 *ttab,
+                                                 float2 *__restrict__ X, int tid)
+{
+    using Gm = FirGeom<D, R, NT, LMAX>;
+    static_assert(NT % Gm::G == 0, "a thread's groups stay in one row");
+    // local group gc holds tile samples 4gc..4gc+3; a partial last group is decoded whole (its bytes are
+    // inside the 16-byte-rounded copy and its slots inside the tile's spare column; nothing reads them)
+    const uint32_t n_loc = (n_dec + 3) >> 2;
+    const uint2 *rp = reinterpret_cast<const uint2 *>(raw) + (lead >> 2) + tid;
+    float4 *xb = reinterpret_cast<float4 *>(X) + (tid & (Gm::G - 1)) * Gm::PITCH + (tid >> Gm::LOG_G);
+    float2 g = make_float2(1.0f, 0.0f);
+    uint64_t W = 0, wstep = 0;
+    uint32_t mk32 = 0;
+    float esc = 0.0f;
+    if (MIX) {
+        const double2 t = ttab[tid];
+        const double ac = lp->ac, as = lp->as;
+        g = make_float2(static_cast<float>(fma(ac, t.x, -__dmul_rn(as, t.y))), static_cast<float>(fma(ac, t.y, __dmul_rn(as, t.x))));
+        const uint64_t m64k = lp->m64k;
+        W = (n_tile0 + static_cast<uint64_t>(4 * tid)) * m64k;
+        wstep = static_cast<uint64_t>(4 * NT) * m64k;
+        mk32 = lp->mk32;
+        esc = lp->esc;
+    }
+    const float2 negk = make_float2(-8388736.0f, -8388736.0f); // -(2^23 + 128)
+    const float2 r1c = make_float2(a.rot[1].x, a.rot[1].x), r1s = make_float2(a.rot[1].y, a.rot[1].y);
+    const float2 r2c = make_float2(a.rot[2].x, a.rot[2].x), r2s = make_float2(a.rot[2].y, a.rot[2].y);
+    const float2 r3c = make_float2(a.rot[3].x, a.rot[3].x), r3s = make_float2(a.rot[3].y, a.rot[3].y);
+    const float2 rsc = make_float2(a.rot_step.x, a.rot_step.x), rss = make_float2(a.rot_step.y, a.rot_step.y);
+    for (uint32_t gc = tid; gc < n_loc; gc += NT, rp += NT, xb += NT / Gm::G) {
+        const uint2 v = *rp;
+        const uint32_t u0 = v.x ^ 0x80808080u, u1 = v.y ^ 0x80808080u;
+        float2 x[4];
+        x[0] = add2(make_float2(__uint_as_float(__byte_perm(u0, 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(u0, 0x4B000000u, 0x7441))), negk);
+        x[1] = add2(make_float2(__uint_as_float(__byte_perm(u0, 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(u0, 0x4B000000u, 0x7443))), negk);
+        x[2] = add2(make_float2(__uint_as_float(__byte_perm(u1, 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(u1, 0x4B000000u, 0x7441))), negk);
+        x[3] = add2(make_float2(__uint_as_float(__byte_perm(u1, 0x4B000000u, 0x7442)), __uint_as_float(__byte_perm(u1, 0x4B000000u, 0x7443))), negk);
+        if (MIX) {
+            const float2 gp = make_float2(-g.y, g.x); // i * g
+            float2 ph[4];
+            ph[0] = g;
+            ph[1] = fma2(gp, r1s, mul2(g, r1c));
+            ph[2] = fma2(gp, r2s, mul2(g, r2c));
+            ph[3] = fma2(gp, r3s, mul2(g, r3c));
+            const uint32_t w0 = static_cast<uint32_t>(W >> 32);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float e = esc * static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i) * mk32));
+                const float c = fmaf(e, ph[i].y, ph[i].x), sn = fmaf(-e, ph[i].x, ph[i].y); // * (1 - i e)
+                x[i] = make_float2(fmaf(x[i].x, c, -x[i].y * sn), fmaf(x[i].x, sn, x[i].y * c));
+            }
+            g = fma2(gp, rss, mul2(g, rsc));
+            W += wstep;
+        }
+        xb[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+        xb[Gm::G * Gm::PITCH] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+    }
+}
+
 // ---------------------------------------------------------------------------- FIR stage
 // Block b of a thread = its local samples s = b*D .. b*D+D-1: pair rows (b mod R)*D/2 + p/2, column tid + b div R.
 template <int D, int R, int NT, int LMAX>
@@ -436,9 +560,15 @@ __global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(co
     constexpr int DR = Gm::DR;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
-    float2 *X = reinterpret_cast<float2 *>(smem + 16);
-    uint8_t *raw0 = smem + 16 + Gm::X_BYTES;
+    LeanPhase *lphase = reinterpret_cast<LeanPhase *>(smem + 16);
+    float2 *X = reinterpret_cast<float2 *>(smem + kSmemHeader);
+    uint8_t *raw0 = smem + kSmemHeader + Gm::X_BYTES;
+    double2 *ttab = reinterpret_cast<double2 *>(raw0 + a.raw_cap); // lean path: e^{i 4t ratio} per thread
     const int tid = threadIdx.x;
+    // FAST, cs8, at most one shift: the lean decode loop (tiles that start off a 4-sample boundary or straddle a
+    // binade of n*ratio take the general one)
+    const bool lean = !EXACT && a.fmt == QD_FMT_CS8 && a.n_shift <= 1;
+    const bool lean_mix = lean && a.n_shift == 1;
     const uint32_t pb = a.fmt == QD_FMT_CF32 ? 8 : (a.fmt == QD_FMT_CS16 ? 4 : 2);
     const bool staged = a.fmt != QD_FMT_CF32; // cf32 tiles are read straight from global memory
 
@@ -446,6 +576,15 @@ __global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(co
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    auto tile_phase = [&](const TileGeo &g) { // thread 0, one tile ahead
+        lean_phase(a, g.n_tile0, static_cast<uint32_t>(g.cnt - 1) * D + a.L + 4, lphase);
+    };
+    if (lean_mix) {
+        double c, s;
+        sincos_f64k(__dmul_rn(static_cast<double>(4 * tid), a.ratio[0]), a.sincos, a.k, c, s);
+        ttab[tid] = make_double2(c, s);
+        if (tid == 0 && blockIdx.x < a.n_tiles) tile_phase(tile_geo<D, Gm::T_OUT>(a, blockIdx.x));
     }
     __syncthreads();
 
@@ -481,7 +620,10 @@ __global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(co
         {
             const uint8_t *raw = staged ? raw0
                                         : reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
-            if ((lead & 3) == 0) {
+            if (!EXACT && lean && (lead & 3) == 0 && (!lean_mix || lphase->ok)) {
+                if (lean_mix) decode_tile_lean<D, R, NT, LMAX, true>(a, raw, lead, n_dec, g.n_tile0, lphase, ttab, X, tid);
+                else decode_tile_lean<D, R, NT, LMAX, false>(a, raw, lead, n_dec, g.n_tile0, lphase, ttab, X, tid);
+            } else if ((lead & 3) == 0) {
                 switch (a.fmt) {
                 case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
                 case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
@@ -499,7 +641,11 @@ __global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(co
         }
         __syncthreads();
         // the raw bytes are consumed: fetch the next tile's while this one is filtered
-        if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x));
+        if (tid == 0 && tile + gridDim.x < a.n_tiles) {
+            const TileGeo gn = tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x);
+            issue(gn);
+            if (lean_mix) tile_phase(gn);
+        }
 
         // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
         if (static_cast<uint32_t>(R * tid) < g.cnt) {
@@ -571,7 +717,7 @@ template <int D, int R, int NT, bool EXACT, int LS>
 static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
 {
     using Gm = FirGeom<D, R, NT, (LS > 0 ? LS : kMaxTapPairs)>;
-    const size_t smem = 16 + Gm::X_BYTES + static_cast<size_t>(a.raw_cap);
+    const size_t smem = kSmemHeader + Gm::X_BYTES + static_cast<size_t>(a.raw_cap) + (EXACT ? 0 : NT * sizeof(double2));
     if (smem > 227 * 1024) return set_error(QD_E_INVALID_ARG, "internal: fused FIR tile needs %zu bytes of shared memory", smem);
     const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
     const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, 4)));
@@ -694,6 +840,13 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
         for (int k = 0; k < 4; k++) a.rot[k] = make_float2(static_cast<float>(cos(k * rsum)), static_cast<float>(sin(k * rsum)));
         const double step = 4.0 * lp.shape.NT * rsum;
         a.rot_step = make_float2(static_cast<float>(cos(step)), static_cast<float>(sin(step)));
+        if (n_shift == 1 && ratios[0] != 0.0 && std::isnormal(ratios[0])) {
+            int ex = 0;
+            const double m = frexp(fabs(ratios[0]), &ex); // |ratio| = m * 2^ex, m in [0.5, 1)
+            a.rmant = static_cast<uint64_t>(ldexp(m, 53));
+            a.rexp = ex - 53;
+            a.rsign = ratios[0] < 0.0 ? -1 : 1;
+        }
     }
     FirTaps taps;
     memset(&taps, 0, sizeof taps);
