@@ -59,6 +59,8 @@ struct FirArgs {
     uint64_t rmant;
     int rexp;
     int rsign;
+    int ncall_log2;   // n_call = 2^ncall_log2, or -1
+    double rot_tile[2]; // contiguous mode: e^{i dn ratio}, dn = raw samples from one tile of a CTA to its next
 };
 
 // Per-tile phase state of the lean FAST decode, computed by one thread while the previous tile is filtered
@@ -222,11 +224,16 @@ __device__ __forceinline__ TileGeo tile_geo(const FirArgs &a, uint64_t tile)
         g.cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(T_OUT), total - g.f0));
         g.out0 = g.f0;
         g.unit = 0;
-        g.u0 = g.f0 / a.n_call;
+        g.u0 = a.ncall_log2 >= 0 ? (g.f0 >> a.ncall_log2) : g.f0 / a.n_call;
         g.n_tile0 = (a.off0 + g.f0) * D + i0;
     } else {
-        g.unit = tile / a.tiles_per_unit;
-        const uint32_t k0 = static_cast<uint32_t>(tile % a.tiles_per_unit) * T_OUT;
+        if (a.n_tiles <= 0xffffffffull) { // 32-bit division
+            const uint32_t u = static_cast<uint32_t>(tile) / a.tiles_per_unit;
+            g.unit = u;
+        } else {
+            g.unit = tile / a.tiles_per_unit;
+        }
+        const uint32_t k0 = static_cast<uint32_t>(tile - g.unit * a.tiles_per_unit) * T_OUT;
         g.cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(T_OUT), a.n_call - k0));
         g.out0 = g.unit * a.n_call + k0;
         g.f0 = 0;
@@ -371,15 +378,22 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
 // the k bits the multiply rounds away.  Those bits are n * rmant mod 2^k: kept left-aligned in a 64-bit
 // integer they advance by one wrapping add per group, and their top word read as a signed fraction of an
 // ulp is the rounding error (ties excepted: they round to even, here always up).
+template <bool STEP>
 __device__ __forceinline__ void lean_phase(const FirArgs &a, uint64_t n0, uint32_t span, LeanPhase *ph)
 {
-    const double nd = __ull2double_rn(n0), r = a.ratio[0];
-    const double p = __dmul_rn(nd, r);
-    const double e = fma(nd, r, -p); // exact product minus the rounded one
-    double c, s;
-    sincos_f64k(p, a.sincos, a.k, c, s);
-    ph->ac = fma(-e, s, c);
-    ph->as = fma(e, c, s);
+    if (STEP) { // the CTA's previous tile lies a fixed distance back: one f64 rotation (a few hundred steps per launch)
+        const double c = ph->ac, s = ph->as, rc = a.rot_tile[0], rs = a.rot_tile[1];
+        ph->ac = fma(c, rc, -__dmul_rn(s, rs));
+        ph->as = fma(c, rs, __dmul_rn(s, rc));
+    } else {
+        const double nd = __ull2double_rn(n0), r = a.ratio[0];
+        const double p = __dmul_rn(nd, r);
+        const double e = fma(nd, r, -p); // exact product minus the rounded one
+        double c, s;
+        sincos_f64k(p, a.sincos, a.k, c, s);
+        ph->ac = fma(-e, s, c);
+        ph->as = fma(e, c, s);
+    }
     const uint64_t M = a.rmant;
     auto bitlen = [&](uint64_t n) {
         const uint64_t hi = __umul64hi(n, M), lo = n * M;
@@ -432,7 +446,8 @@ __device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t
     const float2 r3c = make_float2(a.rot[3].x, a.rot[3].x), r3s = make_float2(a.rot[3].y, a.rot[3].y);
     const float2 rsc = make_float2(a.rot_step.x, a.rot_step.x), rss = make_float2(a.rot_step.y, a.rot_step.y);
     for (uint32_t gc = tid; gc < n_loc; gc += NT, rp += NT, xb += NT / Gm::G) {
-        const uint2 v = *rp;
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(rp)));
         const uint32_t u0 = v.x ^ 0x80808080u, u1 = v.y ^ 0x80808080u;
         float2 x[4];
         x[0] = add2(make_float2(__uint_as_float(__byte_perm(u0, 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(u0, 0x4B000000u, 0x7441))), negk);
@@ -552,8 +567,19 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
     for (; b < NB; ++b) general_block<D, R, NT, LMAX, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
 }
 
+// resident CTAs per SM the kernel is compiled for (register budget) and launched at
 template <int D, int R, int NT, bool EXACT, int LS>
-__global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
+constexpr int ctas_per_sm()
+{
+    if (NT <= 128 && D <= 8) {
+        if (!EXACT && LS > 0) return R <= 2 ? 8 : 5;
+        return 4;
+    }
+    return 2;
+}
+
+template <int D, int R, int NT, bool EXACT, int LS>
+__global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
 {
     constexpr int LMAX = LS > 0 ? LS : kMaxTapPairs;
     using Gm = FirGeom<D, R, NT, LMAX>;
@@ -577,14 +603,16 @@ __global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(co
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    auto tile_phase = [&](const TileGeo &g) { // thread 0, one tile ahead
-        lean_phase(a, g.n_tile0, static_cast<uint32_t>(g.cnt - 1) * D + a.L + 4, lphase);
+    auto tile_phase = [&](const TileGeo &g, bool first) { // thread 0, one tile ahead
+        const uint32_t span = static_cast<uint32_t>(g.cnt - 1) * D + a.L + 4;
+        if (a.contiguous && !first) lean_phase<true>(a, g.n_tile0, span, lphase);
+        else lean_phase<false>(a, g.n_tile0, span, lphase);
     };
     if (lean_mix) {
         double c, s;
         sincos_f64k(__dmul_rn(static_cast<double>(4 * tid), a.ratio[0]), a.sincos, a.k, c, s);
         ttab[tid] = make_double2(c, s);
-        if (tid == 0 && blockIdx.x < a.n_tiles) tile_phase(tile_geo<D, Gm::T_OUT>(a, blockIdx.x));
+        if (tid == 0 && blockIdx.x < a.n_tiles) tile_phase(tile_geo<D, Gm::T_OUT>(a, blockIdx.x), true);
     }
     __syncthreads();
 
@@ -641,11 +669,10 @@ __global__ void __launch_bounds__(NT, ((NT <= 128 && D <= 8) ? 4 : 2)) fk_fir(co
         }
         __syncthreads();
         // the raw bytes are consumed: fetch the next tile's while this one is filtered
-        if (tid == 0 && tile + gridDim.x < a.n_tiles) {
-            const TileGeo gn = tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x);
-            issue(gn);
-            if (lean_mix) tile_phase(gn);
-        }
+        if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x));
+        // the next tile's phase state: another warp's spare lane, so no warp carries both chores into the barrier
+        if (lean_mix && tid == (NT > 32 ? 32 : 0) && tile + gridDim.x < a.n_tiles)
+            tile_phase(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x), false);
 
         // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
         if (static_cast<uint32_t>(R * tid) < g.cnt) {
@@ -720,9 +747,17 @@ static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
     const size_t smem = kSmemHeader + Gm::X_BYTES + static_cast<size_t>(a.raw_cap) + (EXACT ? 0 : NT * sizeof(double2));
     if (smem > 227 * 1024) return set_error(QD_E_INVALID_ARG, "internal: fused FIR tile needs %zu bytes of shared memory", smem);
     const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
-    const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, 4)));
+    const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, std::max(4, ctas_per_sm<D, R, NT, EXACT, LS>()))));
     QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    fk_fir<D, R, NT, EXACT, LS><<<grid, NT, smem, c.stream>>>(a, t);
+    FirArgs b = a;
+    if (!EXACT && a.n_shift == 1) {
+        // exact angle of dn * ratio as p + e (the product's rounding error recovered by an FMA)
+        const double dn = static_cast<double>(static_cast<uint64_t>(grid) * Gm::T_OUT * D);
+        const double p = dn * a.ratio[0], e = fma(dn, a.ratio[0], -p);
+        b.rot_tile[0] = cos(p) - e * sin(p);
+        b.rot_tile[1] = sin(p) + e * cos(p);
+    }
+    fk_fir<D, R, NT, EXACT, LS><<<grid, NT, smem, c.stream>>>(b, t);
     QD_LAUNCHED();
     return QD_OK;
 }
@@ -825,6 +860,10 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     a.S = S;
     a.n_units = n_units;
     a.contiguous = (S == n_call || n_units == 1) ? 1 : 0;
+    a.ncall_log2 = -1;
+    if (is_pow2(n_call))
+        for (int b = 0; b < 64; b++)
+            if ((uint64_t(1) << b) == n_call) a.ncall_log2 = b;
     a.total_out = total_out;
     const uint64_t t_out = static_cast<uint64_t>(R) * lp.shape.NT;
     a.tiles_per_unit = static_cast<uint32_t>((n_call + t_out - 1) / t_out);
