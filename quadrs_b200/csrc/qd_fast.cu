@@ -424,7 +424,8 @@ __device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t
     // local group gc holds tile samples 4gc..4gc+3; a partial last group is decoded whole (its bytes are
     // inside the 16-byte-rounded copy and its slots inside the tile's spare column; nothing reads them)
     const uint32_t n_loc = (n_dec + 3) >> 2;
-    const uint2 *rp = reinterpret_cast<const uint2 *>(raw) + (lead >> 2) + tid;
+    uint32_t rp = smem_u32(raw) + 8u * ((lead >> 2) + static_cast<uint32_t>(tid)); // shared-window address of the thread's group
+    const uint32_t rp_end = smem_u32(raw) + 8u * ((lead >> 2) + n_loc);
     float4 *xb = reinterpret_cast<float4 *>(X) + (tid & (Gm::G - 1)) * Gm::PITCH + (tid >> Gm::LOG_G);
     float2 g = make_float2(1.0f, 0.0f);
     uint64_t W = 0, wstep = 0;
@@ -445,9 +446,10 @@ __device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t
     const float2 r2c = make_float2(a.rot[2].x, a.rot[2].x), r2s = make_float2(a.rot[2].y, a.rot[2].y);
     const float2 r3c = make_float2(a.rot[3].x, a.rot[3].x), r3s = make_float2(a.rot[3].y, a.rot[3].y);
     const float2 rsc = make_float2(a.rot_step.x, a.rot_step.x), rss = make_float2(a.rot_step.y, a.rot_step.y);
-    for (uint32_t gc = tid; gc < n_loc; gc += NT, rp += NT, xb += NT / Gm::G) {
+#pragma unroll 2
+    for (; rp < rp_end; rp += 8u * NT, xb += NT / Gm::G) {
         uint2 v;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(rp)));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(rp));
         const uint32_t u0 = v.x ^ 0x80808080u, u1 = v.y ^ 0x80808080u;
         float2 x[4];
         x[0] = add2(make_float2(__uint_as_float(__byte_perm(u0, 0x4B000000u, 0x7440)), __uint_as_float(__byte_perm(u0, 0x4B000000u, 0x7441))), negk);
@@ -462,11 +464,19 @@ __device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t
             ph[2] = fma2(gp, r2s, mul2(g, r2c));
             ph[3] = fma2(gp, r3s, mul2(g, r3c));
             const uint32_t w0 = static_cast<uint32_t>(W >> 32);
+            float e[4];
+#pragma unroll
+            for (int i = 0; i < 4; i += 2) { // signed fraction of an ulp -> radians, two samples per packed multiply
+                const float2 ee = mul2(make_float2(static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i) * mk32)),
+                                                   static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i + 1) * mk32))),
+                                       make_float2(esc, esc));
+                e[i] = ee.x, e[i + 1] = ee.y;
+            }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const float e = esc * static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i) * mk32));
-                const float c = fmaf(e, ph[i].y, ph[i].x), sn = fmaf(-e, ph[i].x, ph[i].y); // * (1 - i e)
-                x[i] = make_float2(fmaf(x[i].x, c, -x[i].y * sn), fmaf(x[i].x, sn, x[i].y * c));
+                // p = ph * (1 - i e), then (xr + i xi) * p = xr * p + xi * (i p): packed, with broadcast scalars
+                const float2 p = fma2(make_float2(ph[i].y, -ph[i].x), make_float2(e[i], e[i]), ph[i]);
+                x[i] = fma2(make_float2(-p.y, p.x), make_float2(x[i].y, x[i].y), mul2(p, make_float2(x[i].x, x[i].x)));
             }
             g = fma2(gp, rss, mul2(g, rsc));
             W += wstep;
