@@ -55,6 +55,7 @@ struct FirArgs {
     // FAST mode NCO: all leading shifts merged into one rotation of ratio_sum per sample
     float2 rot[4];    // e^{i k ratio_sum}, k = 0..3 (k = 0 unused)
     float2 rot_step;  // e^{i 4*NT ratio_sum}: from one group of a thread to its next
+    float2 rot_stepw; // e^{i 4*32 ratio_sum}: the same when one warp shares the groups (fk_firw)
     // lean cs8 path (one shift): |ratio[0]| = rmant * 2^rexp exactly, rsign = +-1 (0: ratio is zero)
     uint64_t rmant;
     int rexp;
@@ -198,7 +199,10 @@ struct FirGeom {
     static constexpr int LOG_DR = (DR == 16) ? 4 : (DR == 32) ? 5 : 6;
     static constexpr int LOG_G = LOG_DR - 2;
     static constexpr int T_OUT = R * NT;
-    static constexpr int COLS = NT + ((R - 1) * D + LMAX + DR - 1) / DR + 1; // LMAX: longest filter this layout holds
+    // samples the tile's threads touch: whole tap blocks of D for the longest filter this layout holds, plus
+    // the tail of a partial last decode group where one can exist
+    static constexpr int SPAN = (T_OUT - 1) * D + (LMAX + D - 1) / D * D + ((LMAX % 4 || D % 4) ? 3 : 0);
+    static constexpr int COLS = (SPAN + DR - 1) / DR;
     static constexpr int PITCH = pitch_for(G, COLS); // float4 (sample pairs) per row; there are DR/2 rows
     static constexpr size_t X_BYTES = static_cast<size_t>(DR / 2) * PITCH * sizeof(float4);
     static_assert(DR == 16 || DR == 32 || DR == 64, "polyphase period must be 16, 32 or 64");
@@ -414,40 +418,47 @@ __device__ __forceinline__ void lean_phase(const FirArgs &a, uint64_t n0, uint32
     ph->ok = (b0 == b1) ? 1 : 0;
 }
 
-template <int D, int R, int NT, int LMAX, bool MIX>
-__device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
-                                                 uint64_t n_tile0, const LeanPhase *lp, const double2 *ttab,
-                                                 float2 *__restrict__ X, int tid)
+// STRIDE threads share the groups of one decode region (the CTA's tile, or one warp's private part of it);
+// idx is the thread's rank among them, t = e^{i 4 idx ratio} (times the region's offset into the tile),
+// rstep = e^{i 4 STRIDE ratio}.  CHECK_OK: a region that straddles a binade of n*ratio recovers the product's
+// rounding error with an f64 FMA per sample instead of the integer fraction.
+template <class Gm, int STRIDE, bool MIX, bool CHECK_OK>
+__device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr, uint32_t n_dec, uint64_t n0,
+                                            const LeanPhase *lp, double2 t, float2 rstep, float4 *__restrict__ X4, int idx)
 {
-    using Gm = FirGeom<D, R, NT, LMAX>;
-    static_assert(NT % Gm::G == 0, "a thread's groups stay in one row");
-    // local group gc holds tile samples 4gc..4gc+3; a partial last group is decoded whole (its bytes are
-    // inside the 16-byte-rounded copy and its slots inside the tile's spare column; nothing reads them)
+    static_assert(STRIDE % Gm::G == 0, "a thread's groups stay in one row");
+    // local group gc holds region samples 4gc..4gc+3; a partial last group is decoded whole (its bytes are
+    // inside the 16-byte-rounded copy and its slots inside the layout's slack; nothing reads them)
     const uint32_t n_loc = (n_dec + 3) >> 2;
-    uint32_t rp = smem_u32(raw) + 8u * ((lead >> 2) + static_cast<uint32_t>(tid)); // shared-window address of the thread's group
-    const uint32_t rp_end = smem_u32(raw) + 8u * ((lead >> 2) + n_loc);
-    float4 *xb = reinterpret_cast<float4 *>(X) + (tid & (Gm::G - 1)) * Gm::PITCH + (tid >> Gm::LOG_G);
+    uint32_t rp = raw_addr + 8u * static_cast<uint32_t>(idx); // shared-window address of the thread's group
+    const uint32_t rp_end = raw_addr + 8u * n_loc;
+    float4 *xb = X4 + (idx & (Gm::G - 1)) * Gm::PITCH + (idx >> Gm::LOG_G);
     float2 g = make_float2(1.0f, 0.0f);
     uint64_t W = 0, wstep = 0;
     uint32_t mk32 = 0;
     float esc = 0.0f;
+    bool ok = true;
+    double nd = 0.0;
     if (MIX) {
-        const double2 t = ttab[tid];
         const double ac = lp->ac, as = lp->as;
         g = make_float2(static_cast<float>(fma(ac, t.x, -__dmul_rn(as, t.y))), static_cast<float>(fma(ac, t.y, __dmul_rn(as, t.x))));
         const uint64_t m64k = lp->m64k;
-        W = (n_tile0 + static_cast<uint64_t>(4 * tid)) * m64k;
-        wstep = static_cast<uint64_t>(4 * NT) * m64k;
+        W = (n0 + static_cast<uint64_t>(4 * idx)) * m64k;
+        wstep = static_cast<uint64_t>(4 * STRIDE) * m64k;
         mk32 = lp->mk32;
         esc = lp->esc;
+        if (CHECK_OK) {
+            ok = lp->ok != 0;
+            nd = __ull2double_rn(n0 + static_cast<uint64_t>(4 * idx));
+        }
     }
     const float2 negk = make_float2(-8388736.0f, -8388736.0f); // -(2^23 + 128)
     const float2 r1c = make_float2(a.rot[1].x, a.rot[1].x), r1s = make_float2(a.rot[1].y, a.rot[1].y);
     const float2 r2c = make_float2(a.rot[2].x, a.rot[2].x), r2s = make_float2(a.rot[2].y, a.rot[2].y);
     const float2 r3c = make_float2(a.rot[3].x, a.rot[3].x), r3s = make_float2(a.rot[3].y, a.rot[3].y);
-    const float2 rsc = make_float2(a.rot_step.x, a.rot_step.x), rss = make_float2(a.rot_step.y, a.rot_step.y);
+    const float2 rsc = make_float2(rstep.x, rstep.x), rss = make_float2(rstep.y, rstep.y);
 #pragma unroll 2
-    for (; rp < rp_end; rp += 8u * NT, xb += NT / Gm::G) {
+    for (; rp < rp_end; rp += 8u * STRIDE, xb += STRIDE / Gm::G) {
         uint2 v;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(rp));
         const uint32_t u0 = v.x ^ 0x80808080u, u1 = v.y ^ 0x80808080u;
@@ -463,14 +474,22 @@ __device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t
             ph[1] = fma2(gp, r1s, mul2(g, r1c));
             ph[2] = fma2(gp, r2s, mul2(g, r2c));
             ph[3] = fma2(gp, r3s, mul2(g, r3c));
-            const uint32_t w0 = static_cast<uint32_t>(W >> 32);
             float e[4];
+            if (!CHECK_OK || ok) {
+                const uint32_t w0 = static_cast<uint32_t>(W >> 32);
 #pragma unroll
-            for (int i = 0; i < 4; i += 2) { // signed fraction of an ulp -> radians, two samples per packed multiply
-                const float2 ee = mul2(make_float2(static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i) * mk32)),
-                                                   static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i + 1) * mk32))),
-                                       make_float2(esc, esc));
-                e[i] = ee.x, e[i + 1] = ee.y;
+                for (int i = 0; i < 4; i += 2) { // signed fraction of an ulp -> radians, two samples per packed multiply
+                    const float2 ee = mul2(make_float2(static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i) * mk32)),
+                                                       static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i + 1) * mk32))),
+                                           make_float2(esc, esc));
+                    e[i] = ee.x, e[i + 1] = ee.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const double ni = __dadd_rn(nd, static_cast<double>(i));
+                    e[i] = static_cast<float>(fma(ni, a.ratio[0], -__dmul_rn(ni, a.ratio[0])));
+                }
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -480,10 +499,21 @@ __device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t
             }
             g = fma2(gp, rss, mul2(g, rsc));
             W += wstep;
+            if (CHECK_OK) nd = __dadd_rn(nd, static_cast<double>(4 * STRIDE));
         }
         xb[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
         xb[Gm::G * Gm::PITCH] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
     }
+}
+
+template <int D, int R, int NT, int LMAX, bool MIX>
+__device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
+                                                 uint64_t n_tile0, const LeanPhase *lp, const double2 *ttab,
+                                                 float2 *__restrict__ X, int tid)
+{
+    decode_lean<FirGeom<D, R, NT, LMAX>, NT, MIX, false>(a, smem_u32(raw) + 8u * (lead >> 2), n_dec, n_tile0, lp,
+                                                         MIX ? ttab[tid] : make_double2(1.0, 0.0), a.rot_step,
+                                                         reinterpret_cast<float4 *>(X), tid);
 }
 
 // ---------------------------------------------------------------------------- FIR stage
@@ -577,13 +607,64 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
     for (; b < NB; ++b) general_block<D, R, NT, LMAX, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
 }
 
+// FIR + store of one tile: thread `tid` of the tile owns outputs R*tid .. R*tid+R-1; its samples sit in the
+// layout X (geometry FirGeom<D, R, NTG, LMAX>) from column xidx on
+template <int D, int R, int NTG, int LMAX, bool EXACT, int LS>
+__device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, const TileGeo &g, const float2 *__restrict__ X,
+                                 int xidx, int tid)
+{
+    if (static_cast<uint32_t>(R * tid) < g.cnt) {
+        // the unit's raw buffer ends at (unit_top0 + n_call)*D + L: later samples do not exist for
+        // this read (filter.rs:68-71) and the ascending tap loop stops there
+        uint64_t unit_top0;
+        if (a.contiguous) {
+            // one division per tile (g.u0 = f0 / n_call); a thread's outputs start `rel` past that unit
+            uint64_t rel = g.f0 - g.u0 * a.n_call + static_cast<uint64_t>(R * tid);
+            uint64_t un = g.u0;
+            while (rel >= a.n_call) { // the tile runs over one or more unit boundaries
+                rel -= a.n_call;
+                un++;
+            }
+            unit_top0 = a.off0 + un * a.n_call;
+        } else {
+            unit_top0 = a.off0 + g.unit * a.S;
+        }
+        const uint64_t raw_end = (unit_top0 + a.n_call) * D + a.L;
+        const int64_t s_lim = static_cast<int64_t>(raw_end - g.n_tile0) - static_cast<int64_t>(tid) * (D * R);
+        const int L = LS > 0 ? LS : static_cast<int>(a.L);
+        const int s_total = (R - 1) * D + L;
+        const int Q = (L + D - 1) / D, Lrem = L - (Q - 1) * D;
+        const float2 one = a.one;
+
+        float2 acc[R];
+    #pragma unroll
+        for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f); // Complex::zero(), filter.rs:112
+
+        if (LS > 0 && s_lim >= s_total) {
+            fir_static<D, R, NTG, LMAX, EXACT, (LS > 0 ? LS : 1)>(X, xidx, taps, one, acc);
+        } else { // also the tail of a read: outputs whose taps run past the end of the unit's raw buffer
+            const int s_end = static_cast<int>(min(static_cast<int64_t>(s_total), s_lim));
+            fir_dynamic<D, R, NTG, LMAX, EXACT>(X, xidx, Q, Lrem, s_end, taps, one, acc);
+        }
+        float2 *o = a.out + g.out0 + static_cast<uint64_t>(R * tid);
+        if (R % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+    #pragma unroll
+            for (int r = 0; r < R; r += 2)
+                *reinterpret_cast<float4 *>(o + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+        } else {
+    #pragma unroll
+            for (int r = 0; r < R; r++) o[r] = acc[r];
+        }
+    }
+}
+
 // resident CTAs per SM the kernel is compiled for (register budget) and launched at
 template <int D, int R, int NT, bool EXACT, int LS>
 constexpr int ctas_per_sm()
 {
     if (NT <= 128 && D <= 8) {
-        if (!EXACT && LS > 0) return R <= 2 ? 8 : 5;
-        return 4;
+        if (!EXACT && LS > 0) return (R <= 2 ? 8 : 5) * (128 / NT);
+        return 4 * (128 / NT);
     }
     return 2;
 }
@@ -593,7 +674,6 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
 {
     constexpr int LMAX = LS > 0 ? LS : kMaxTapPairs;
     using Gm = FirGeom<D, R, NT, LMAX>;
-    constexpr int DR = Gm::DR;
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
     LeanPhase *lphase = reinterpret_cast<LeanPhase *>(smem + 16);
@@ -685,50 +765,103 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
             tile_phase(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x), false);
 
         // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
-        if (static_cast<uint32_t>(R * tid) < g.cnt) {
-            // the unit's raw buffer ends at (unit_top0 + n_call)*D + L: later samples do not exist for
-            // this read (filter.rs:68-71) and the ascending tap loop stops there
-            uint64_t unit_top0;
-            if (a.contiguous) {
-                // one division per tile (g.u0 = f0 / n_call); a thread's outputs start `rel` past that unit
-                uint64_t rel = g.f0 - g.u0 * a.n_call + static_cast<uint64_t>(R * tid);
-                uint64_t un = g.u0;
-                while (rel >= a.n_call) { // the tile runs over one or more unit boundaries
-                    rel -= a.n_call;
-                    un++;
-                }
-                unit_top0 = a.off0 + un * a.n_call;
-            } else {
-                unit_top0 = a.off0 + g.unit * a.S;
-            }
-            const uint64_t raw_end = (unit_top0 + a.n_call) * D + a.L;
-            const int64_t s_lim = static_cast<int64_t>(raw_end - g.n_tile0) - static_cast<int64_t>(tid) * DR;
-            const int L = LS > 0 ? LS : static_cast<int>(a.L);
-            const int s_total = (R - 1) * D + L;
-            const int Q = (L + D - 1) / D, Lrem = L - (Q - 1) * D;
-            const float2 one = a.one;
+        fir_tile<D, R, NT, LMAX, EXACT, LS>(a, taps, g, X, tid, tid);
+        __syncthreads();
+    }
+}
 
-            float2 acc[R];
-#pragma unroll
-            for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f); // Complex::zero(), filter.rs:112
+// ---------------------------------------------------------------------------- warp-private tiles (FAST cs8)
+// The same tile, but each of the CTA's four warps decodes the quarter it filters (plus its own copy of the
+// L - D samples it needs from the next quarter) into a layout of its own, so there is no CTA-wide barrier:
+// the warps only meet at the raw bytes.  The last warp to finish reading them publishes the next tile's phase
+// state and issues its bulk copy; everyone waits on that copy's mbarrier.  Every tile starts on a 4-sample
+// boundary (checked on the host), and a tile that straddles a binade of n*ratio takes the f64 branch of the
+// decode loop.
+constexpr int kWarpsW = 4;
 
-            if (LS > 0 && s_lim >= s_total) {
-                fir_static<D, R, NT, LMAX, EXACT, (LS > 0 ? LS : 1)>(X, tid, taps, one, acc);
-            } else { // also the tail of a read: outputs whose taps run past the end of the unit's raw buffer
-                const int s_end = static_cast<int>(min(static_cast<int64_t>(s_total), s_lim));
-                fir_dynamic<D, R, NT, LMAX, EXACT>(X, tid, Q, Lrem, s_end, taps, one, acc);
-            }
-            float2 *o = a.out + g.out0 + static_cast<uint64_t>(R * tid);
-            if (R % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-#pragma unroll
-                for (int r = 0; r < R; r += 2)
-                    *reinterpret_cast<float4 *>(o + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; r++) o[r] = acc[r];
+template <int D, int R, int LS>
+__global__ void __launch_bounds__(32 * kWarpsW, 5) fk_firw(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
+{
+    constexpr int LMAX = LS > 0 ? LS : kMaxTapPairs;
+    constexpr int NT = 32 * kWarpsW;
+    using Gw = FirGeom<D, R, 32, LMAX>;      // one warp's layout
+    constexpr int T_OUT = R * NT;            // outputs per tile, as fk_fir<D, R, 128>
+    constexpr int WS = 32 * R * D;           // raw samples between the warps' parts
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
+    uint32_t *consumed = reinterpret_cast<uint32_t *>(smem + 8);
+    LeanPhase *lphase = reinterpret_cast<LeanPhase *>(smem + 16);
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    float2 *Xw = reinterpret_cast<float2 *>(smem + kSmemHeader + static_cast<size_t>(w) * Gw::X_BYTES);
+    uint8_t *raw0 = smem + kSmemHeader + kWarpsW * Gw::X_BYTES;
+    const bool mix = a.n_shift == 1;
+    const uint32_t L = LS > 0 ? LS : a.L;
+    const uint32_t wspan = (32 * R - 1) * D + L; // samples one warp decodes
+
+    auto tile_phase = [&](const TileGeo &g, bool first) {
+        const uint32_t span = static_cast<uint32_t>(g.cnt - 1) * D + L + 4;
+        if (a.contiguous && !first) lean_phase<true>(a, g.n_tile0, span, lphase);
+        else lean_phase<false>(a, g.n_tile0, span, lphase);
+    };
+    auto issue = [&](const TileGeo &g) { // tiles start on an 8-byte boundary; the copy is widened to 16
+        const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + L;
+        const uint64_t n_dec = min(span, a.src_end - g.n_tile0);
+        const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * 2;
+        const uint8_t *abeg = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
+        const uintptr_t gend = reinterpret_cast<uintptr_t>(gbeg + n_dec * 2);
+        const uint32_t bytes = static_cast<uint32_t>(((gend + 15) & ~uintptr_t(15)) - reinterpret_cast<uintptr_t>(abeg));
+        mbar_expect_tx(&mbar[0], bytes);
+        bulk_g2s(raw0, abeg, bytes, &mbar[0]);
+    };
+
+    // this thread's offset into the tile, as a phasor: e^{i (w*WS + 4*lane) ratio}
+    double2 tph = make_double2(1.0, 0.0);
+    if (mix) sincos_f64k(__dmul_rn(static_cast<double>(w * WS + 4 * lane), a.ratio[0]), a.sincos, a.k, tph.x, tph.y);
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        *consumed = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (blockIdx.x < a.n_tiles) {
+            const TileGeo g0 = tile_geo<D, T_OUT>(a, blockIdx.x);
+            if (mix) tile_phase(g0, true);
+            issue(g0);
+        }
+    }
+    __syncthreads();
+
+    uint32_t it = 0;
+    for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+        const TileGeo g = tile_geo<D, T_OUT>(a, tile);
+        const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + L;
+        const uint32_t n_dec = static_cast<uint32_t>(min(span, a.src_end - g.n_tile0));
+        const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * 2;
+        const uint32_t lead_bytes = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gbeg) & 15); // 0 or 8
+
+        mbar_wait(&mbar[0], it & 1);
+        {
+            const int n_w = min(static_cast<int>(n_dec) - w * WS, static_cast<int>(wspan));
+            const uint32_t raw_addr = smem_u32(raw0) + lead_bytes + 2u * static_cast<uint32_t>(w * WS);
+            const uint64_t n0 = g.n_tile0 + static_cast<uint64_t>(w * WS);
+            if (n_w > 0) {
+                if (mix) decode_lean<Gw, 32, true, true>(a, raw_addr, static_cast<uint32_t>(n_w), n0, lphase, tph, a.rot_stepw, reinterpret_cast<float4 *>(Xw), lane);
+                else decode_lean<Gw, 32, false, false>(a, raw_addr, static_cast<uint32_t>(n_w), n0, lphase, tph, a.rot_stepw, reinterpret_cast<float4 *>(Xw), lane);
             }
         }
-        __syncthreads();
+        __syncwarp();
+        if (lane == 0) {
+            // the raw bytes (and the phase state) of this tile are consumed once all four warps pass here
+            if (atomicAdd(consumed, 1u) == kWarpsW - 1) {
+                *consumed = 0;
+                if (tile + gridDim.x < a.n_tiles) {
+                    const TileGeo gn = tile_geo<D, T_OUT>(a, tile + gridDim.x);
+                    if (mix) tile_phase(gn, false);
+                    issue(gn); // the arrive on the mbarrier releases the two stores above to its waiters
+                }
+            }
+        }
+        __syncwarp();
+        fir_tile<D, R, 32, LMAX, false, LS>(a, taps, g, Xw, lane, tid);
+        __syncwarp(); // the warp's layout is rewritten by its next decode
     }
 }
 
@@ -757,7 +890,7 @@ static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
     const size_t smem = kSmemHeader + Gm::X_BYTES + static_cast<size_t>(a.raw_cap) + (EXACT ? 0 : NT * sizeof(double2));
     if (smem > 227 * 1024) return set_error(QD_E_INVALID_ARG, "internal: fused FIR tile needs %zu bytes of shared memory", smem);
     const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
-    const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, std::max(4, ctas_per_sm<D, R, NT, EXACT, LS>()))));
+    const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, ctas_per_sm<D, R, NT, EXACT, LS>())));
     QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     FirArgs b = a;
     if (!EXACT && a.n_shift == 1) {
@@ -772,10 +905,39 @@ static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
     return QD_OK;
 }
 
+template <int D, int R, int LS>
+static int launch_firw(Chain &c, const FirArgs &a, const FirTaps &t)
+{
+    using Gw = FirGeom<D, R, 32, LS>;
+    constexpr int NT = 32 * kWarpsW;
+    const size_t smem = kSmemHeader + kWarpsW * Gw::X_BYTES + static_cast<size_t>(a.raw_cap);
+    const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
+    const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, 5)));
+    QD_CUDA(cudaFuncSetAttribute(fk_firw<D, R, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    FirArgs b = a;
+    if (a.n_shift == 1) {
+        const double dn = static_cast<double>(static_cast<uint64_t>(grid) * R * NT * D);
+        const double p = dn * a.ratio[0], e = fma(dn, a.ratio[0], -p);
+        b.rot_tile[0] = cos(p) - e * sin(p);
+        b.rot_tile[1] = sin(p) + e * cos(p);
+    }
+    fk_firw<D, R, LS><<<grid, NT, smem, c.stream>>>(b, t);
+    QD_LAUNCHED();
+    return QD_OK;
+}
+
 // LS = 40 is the reference's default filter (args.rs:165: `None => 40`), specialised at compile time
 template <int D, int R, int NT>
 static int launch_fir_dr(Chain &c, const FirArgs &a, const FirTaps &t, bool exact)
 {
+    if constexpr (NT == 32 * kWarpsW && D % 4 == 0) {
+        if (!exact && a.L == 40 && a.fmt == QD_FMT_CS8 && a.n_shift <= 1 && c.use_firw) {
+            // warp-private tiles: every tile must start on a 4-sample (8-byte) boundary of the capture
+            const uint64_t n_first = a.off0 * D + (a.L - a.L / 2);
+            const uintptr_t first = reinterpret_cast<uintptr_t>(a.src) + (n_first - a.src_base) * 2;
+            if (first % 8 == 0) return launch_firw<D, R, 40>(c, a, t);
+        }
+    }
     if (a.L == 40) return exact ? launch_fir_k<D, R, NT, true, 40>(c, a, t) : launch_fir_k<D, R, NT, false, 40>(c, a, t);
     return exact ? launch_fir_k<D, R, NT, true, 0>(c, a, t) : launch_fir_k<D, R, NT, false, 0>(c, a, t);
 }
@@ -889,6 +1051,7 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
         for (int k = 0; k < 4; k++) a.rot[k] = make_float2(static_cast<float>(cos(k * rsum)), static_cast<float>(sin(k * rsum)));
         const double step = 4.0 * lp.shape.NT * rsum;
         a.rot_step = make_float2(static_cast<float>(cos(step)), static_cast<float>(sin(step)));
+        a.rot_stepw = make_float2(static_cast<float>(cos(128.0 * rsum)), static_cast<float>(sin(128.0 * rsum)));
         if (n_shift == 1 && ratios[0] != 0.0 && std::isnormal(ratios[0])) {
             int ex = 0;
             const double m = frexp(fabs(ratios[0]), &ex); // |ratio| = m * 2^ex, m in [0.5, 1)
