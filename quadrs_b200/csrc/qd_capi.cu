@@ -272,7 +272,6 @@ int qd_chain_set_option(qd_chain *c, const char *key, int64_t value)
     if (!c || !key) return set_error(QD_E_INVALID_ARG, "null argument");
     std::lock_guard<std::mutex> lk(c->mu);
     if (!strcmp(key, "use_fast")) c->use_fast = value != 0;
-    else if (!strcmp(key, "use_firw")) c->use_firw = value != 0;
     else if (!strcmp(key, "segment_bytes") && value > 0) c->segment_bytes = static_cast<size_t>(value);
     else if (!strcmp(key, "scratch_budget") && value > 0) c->scratch_budget = static_cast<size_t>(value);
     else return set_error(QD_E_INVALID_ARG, "unknown option %s=%lld", key, (long long)value);

@@ -55,7 +55,6 @@ struct FirArgs {
     // FAST mode NCO: all leading shifts merged into one rotation of ratio_sum per sample
     float2 rot[4];    // e^{i k ratio_sum}, k = 0..3 (k = 0 unused)
     float2 rot_step;  // e^{i 4*NT ratio_sum}: from one group of a thread to its next
-    float2 rot_stepw; // e^{i 4*32 ratio_sum}: the same when one warp shares the groups (fk_firw)
     // lean cs8 path (one shift): |ratio[0]| = rmant * 2^rexp exactly, rsign = +-1 (0: ratio is zero)
     uint64_t rmant;
     int rexp;
@@ -420,11 +419,17 @@ __device__ __forceinline__ void lean_phase(const FirArgs &a, uint64_t n0, uint32
 
 // STRIDE threads share the groups of one decode region (the CTA's tile, or one warp's private part of it);
 // idx is the thread's rank among them, t = e^{i 4 idx ratio} (times the region's offset into the tile),
-// rstep = e^{i 4 STRIDE ratio}.  CHECK_OK: a region that straddles a binade of n*ratio recovers the product's
-// rounding error with an f64 FMA per sample instead of the integer fraction.
-template <class Gm, int STRIDE, bool MIX, bool CHECK_OK>
+// rstep = e^{i 4 STRIDE ratio}.
+struct LeanParams {
+    float2 g0;      // phasor of the thread's first sample (exact product)
+    uint64_t m64k;  // see LeanPhase
+    uint32_t mk32;
+    float esc;
+};
+
+template <class Gm, int STRIDE, bool MIX>
 __device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr, uint32_t n_dec, uint64_t n0,
-                                            const LeanPhase *lp, double2 t, float2 rstep, float4 *__restrict__ X4, int idx)
+                                            const LeanParams &lp, float2 rstep, float4 *__restrict__ X4, int idx)
 {
     static_assert(STRIDE % Gm::G == 0, "a thread's groups stay in one row");
     // local group gc holds region samples 4gc..4gc+3; a partial last group is decoded whole (its bytes are
@@ -437,20 +442,12 @@ __device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr,
     uint64_t W = 0, wstep = 0;
     uint32_t mk32 = 0;
     float esc = 0.0f;
-    bool ok = true;
-    double nd = 0.0;
     if (MIX) {
-        const double ac = lp->ac, as = lp->as;
-        g = make_float2(static_cast<float>(fma(ac, t.x, -__dmul_rn(as, t.y))), static_cast<float>(fma(ac, t.y, __dmul_rn(as, t.x))));
-        const uint64_t m64k = lp->m64k;
-        W = (n0 + static_cast<uint64_t>(4 * idx)) * m64k;
-        wstep = static_cast<uint64_t>(4 * STRIDE) * m64k;
-        mk32 = lp->mk32;
-        esc = lp->esc;
-        if (CHECK_OK) {
-            ok = lp->ok != 0;
-            nd = __ull2double_rn(n0 + static_cast<uint64_t>(4 * idx));
-        }
+        g = lp.g0;
+        W = (n0 + static_cast<uint64_t>(4 * idx)) * lp.m64k;
+        wstep = static_cast<uint64_t>(4 * STRIDE) * lp.m64k;
+        mk32 = lp.mk32;
+        esc = lp.esc;
     }
     const float2 negk = make_float2(-8388736.0f, -8388736.0f); // -(2^23 + 128)
     const float2 r1c = make_float2(a.rot[1].x, a.rot[1].x), r1s = make_float2(a.rot[1].y, a.rot[1].y);
@@ -475,21 +472,13 @@ __device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr,
             ph[2] = fma2(gp, r2s, mul2(g, r2c));
             ph[3] = fma2(gp, r3s, mul2(g, r3c));
             float e[4];
-            if (!CHECK_OK || ok) {
-                const uint32_t w0 = static_cast<uint32_t>(W >> 32);
+            const uint32_t w0 = static_cast<uint32_t>(W >> 32);
 #pragma unroll
-                for (int i = 0; i < 4; i += 2) { // signed fraction of an ulp -> radians, two samples per packed multiply
-                    const float2 ee = mul2(make_float2(static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i) * mk32)),
-                                                       static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i + 1) * mk32))),
-                                           make_float2(esc, esc));
-                    e[i] = ee.x, e[i + 1] = ee.y;
-                }
-            } else {
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const double ni = __dadd_rn(nd, static_cast<double>(i));
-                    e[i] = static_cast<float>(fma(ni, a.ratio[0], -__dmul_rn(ni, a.ratio[0])));
-                }
+            for (int i = 0; i < 4; i += 2) { // signed fraction of an ulp -> radians, two samples per packed multiply
+                const float2 ee = mul2(make_float2(static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i) * mk32)),
+                                                   static_cast<float>(static_cast<int>(w0 + static_cast<uint32_t>(i + 1) * mk32))),
+                                       make_float2(esc, esc));
+                e[i] = ee.x, e[i + 1] = ee.y;
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
@@ -499,7 +488,6 @@ __device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr,
             }
             g = fma2(gp, rss, mul2(g, rsc));
             W += wstep;
-            if (CHECK_OK) nd = __dadd_rn(nd, static_cast<double>(4 * STRIDE));
         }
         xb[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
         xb[Gm::G * Gm::PITCH] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
@@ -511,8 +499,16 @@ __device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t
                                                  uint64_t n_tile0, const LeanPhase *lp, const double2 *ttab,
                                                  float2 *__restrict__ X, int tid)
 {
-    decode_lean<FirGeom<D, R, NT, LMAX>, NT, MIX, false>(a, smem_u32(raw) + 8u * (lead >> 2), n_dec, n_tile0, lp,
-                                                         MIX ? ttab[tid] : make_double2(1.0, 0.0), a.rot_step,
+    LeanParams q;
+    q.g0 = make_float2(1.0f, 0.0f);
+    q.m64k = 0, q.mk32 = 0, q.esc = 0.0f;
+    if (MIX) {
+        const double2 t = ttab[tid];
+        const double ac = lp->ac, as = lp->as;
+        q.g0 = make_float2(static_cast<float>(fma(ac, t.x, -__dmul_rn(as, t.y))), static_cast<float>(fma(ac, t.y, __dmul_rn(as, t.x))));
+        q.m64k = lp->m64k, q.mk32 = lp->mk32, q.esc = lp->esc;
+    }
+    decode_lean<FirGeom<D, R, NT, LMAX>, NT, MIX>(a, smem_u32(raw) + 8u * (lead >> 2), n_dec, n_tile0, q, a.rot_step,
                                                          reinterpret_cast<float4 *>(X), tid);
 }
 
@@ -770,101 +766,6 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
     }
 }
 
-// ---------------------------------------------------------------------------- warp-private tiles (FAST cs8)
-// The same tile, but each of the CTA's four warps decodes the quarter it filters (plus its own copy of the
-// L - D samples it needs from the next quarter) into a layout of its own, so there is no CTA-wide barrier:
-// the warps only meet at the raw bytes.  The last warp to finish reading them publishes the next tile's phase
-// state and issues its bulk copy; everyone waits on that copy's mbarrier.  Every tile starts on a 4-sample
-// boundary (checked on the host), and a tile that straddles a binade of n*ratio takes the f64 branch of the
-// decode loop.
-constexpr int kWarpsW = 4;
-
-template <int D, int R, int LS>
-__global__ void __launch_bounds__(32 * kWarpsW, 5) fk_firw(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
-{
-    constexpr int LMAX = LS > 0 ? LS : kMaxTapPairs;
-    constexpr int NT = 32 * kWarpsW;
-    using Gw = FirGeom<D, R, 32, LMAX>;      // one warp's layout
-    constexpr int T_OUT = R * NT;            // outputs per tile, as fk_fir<D, R, 128>
-    constexpr int WS = 32 * R * D;           // raw samples between the warps' parts
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem);
-    uint32_t *consumed = reinterpret_cast<uint32_t *>(smem + 8);
-    LeanPhase *lphase = reinterpret_cast<LeanPhase *>(smem + 16);
-    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-    float2 *Xw = reinterpret_cast<float2 *>(smem + kSmemHeader + static_cast<size_t>(w) * Gw::X_BYTES);
-    uint8_t *raw0 = smem + kSmemHeader + kWarpsW * Gw::X_BYTES;
-    const bool mix = a.n_shift == 1;
-    const uint32_t L = LS > 0 ? LS : a.L;
-    const uint32_t wspan = (32 * R - 1) * D + L; // samples one warp decodes
-
-    auto tile_phase = [&](const TileGeo &g, bool first) {
-        const uint32_t span = static_cast<uint32_t>(g.cnt - 1) * D + L + 4;
-        if (a.contiguous && !first) lean_phase<true>(a, g.n_tile0, span, lphase);
-        else lean_phase<false>(a, g.n_tile0, span, lphase);
-    };
-    auto issue = [&](const TileGeo &g) { // tiles start on an 8-byte boundary; the copy is widened to 16
-        const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + L;
-        const uint64_t n_dec = min(span, a.src_end - g.n_tile0);
-        const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * 2;
-        const uint8_t *abeg = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
-        const uintptr_t gend = reinterpret_cast<uintptr_t>(gbeg + n_dec * 2);
-        const uint32_t bytes = static_cast<uint32_t>(((gend + 15) & ~uintptr_t(15)) - reinterpret_cast<uintptr_t>(abeg));
-        mbar_expect_tx(&mbar[0], bytes);
-        bulk_g2s(raw0, abeg, bytes, &mbar[0]);
-    };
-
-    // this thread's offset into the tile, as a phasor: e^{i (w*WS + 4*lane) ratio}
-    double2 tph = make_double2(1.0, 0.0);
-    if (mix) sincos_f64k(__dmul_rn(static_cast<double>(w * WS + 4 * lane), a.ratio[0]), a.sincos, a.k, tph.x, tph.y);
-    if (tid == 0) {
-        mbar_init(&mbar[0], 1);
-        *consumed = 0;
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if (blockIdx.x < a.n_tiles) {
-            const TileGeo g0 = tile_geo<D, T_OUT>(a, blockIdx.x);
-            if (mix) tile_phase(g0, true);
-            issue(g0);
-        }
-    }
-    __syncthreads();
-
-    uint32_t it = 0;
-    for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const TileGeo g = tile_geo<D, T_OUT>(a, tile);
-        const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + L;
-        const uint32_t n_dec = static_cast<uint32_t>(min(span, a.src_end - g.n_tile0));
-        const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * 2;
-        const uint32_t lead_bytes = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gbeg) & 15); // 0 or 8
-
-        mbar_wait(&mbar[0], it & 1);
-        {
-            const int n_w = min(static_cast<int>(n_dec) - w * WS, static_cast<int>(wspan));
-            const uint32_t raw_addr = smem_u32(raw0) + lead_bytes + 2u * static_cast<uint32_t>(w * WS);
-            const uint64_t n0 = g.n_tile0 + static_cast<uint64_t>(w * WS);
-            if (n_w > 0) {
-                if (mix) decode_lean<Gw, 32, true, true>(a, raw_addr, static_cast<uint32_t>(n_w), n0, lphase, tph, a.rot_stepw, reinterpret_cast<float4 *>(Xw), lane);
-                else decode_lean<Gw, 32, false, false>(a, raw_addr, static_cast<uint32_t>(n_w), n0, lphase, tph, a.rot_stepw, reinterpret_cast<float4 *>(Xw), lane);
-            }
-        }
-        __syncwarp();
-        if (lane == 0) {
-            // the raw bytes (and the phase state) of this tile are consumed once all four warps pass here
-            if (atomicAdd(consumed, 1u) == kWarpsW - 1) {
-                *consumed = 0;
-                if (tile + gridDim.x < a.n_tiles) {
-                    const TileGeo gn = tile_geo<D, T_OUT>(a, tile + gridDim.x);
-                    if (mix) tile_phase(gn, false);
-                    issue(gn); // the arrive on the mbarrier releases the two stores above to its waiters
-                }
-            }
-        }
-        __syncwarp();
-        fir_tile<D, R, 32, LMAX, false, LS>(a, taps, g, Xw, lane, tid);
-        __syncwarp(); // the warp's layout is rewritten by its next decode
-    }
-}
-
 // ---------------------------------------------------------------------------- host side
 
 // (decimate) -> outputs per thread R and threads per CTA; R * NT * D ~ 8192 raw samples per tile
@@ -905,39 +806,10 @@ static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
     return QD_OK;
 }
 
-template <int D, int R, int LS>
-static int launch_firw(Chain &c, const FirArgs &a, const FirTaps &t)
-{
-    using Gw = FirGeom<D, R, 32, LS>;
-    constexpr int NT = 32 * kWarpsW;
-    const size_t smem = kSmemHeader + kWarpsW * Gw::X_BYTES + static_cast<size_t>(a.raw_cap);
-    const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
-    const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, 5)));
-    QD_CUDA(cudaFuncSetAttribute(fk_firw<D, R, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    FirArgs b = a;
-    if (a.n_shift == 1) {
-        const double dn = static_cast<double>(static_cast<uint64_t>(grid) * R * NT * D);
-        const double p = dn * a.ratio[0], e = fma(dn, a.ratio[0], -p);
-        b.rot_tile[0] = cos(p) - e * sin(p);
-        b.rot_tile[1] = sin(p) + e * cos(p);
-    }
-    fk_firw<D, R, LS><<<grid, NT, smem, c.stream>>>(b, t);
-    QD_LAUNCHED();
-    return QD_OK;
-}
-
 // LS = 40 is the reference's default filter (args.rs:165: `None => 40`), specialised at compile time
 template <int D, int R, int NT>
 static int launch_fir_dr(Chain &c, const FirArgs &a, const FirTaps &t, bool exact)
 {
-    if constexpr (NT == 32 * kWarpsW && D % 4 == 0) {
-        if (!exact && a.L == 40 && a.fmt == QD_FMT_CS8 && a.n_shift <= 1 && c.use_firw) {
-            // warp-private tiles: every tile must start on a 4-sample (8-byte) boundary of the capture
-            const uint64_t n_first = a.off0 * D + (a.L - a.L / 2);
-            const uintptr_t first = reinterpret_cast<uintptr_t>(a.src) + (n_first - a.src_base) * 2;
-            if (first % 8 == 0) return launch_firw<D, R, 40>(c, a, t);
-        }
-    }
     if (a.L == 40) return exact ? launch_fir_k<D, R, NT, true, 40>(c, a, t) : launch_fir_k<D, R, NT, false, 40>(c, a, t);
     return exact ? launch_fir_k<D, R, NT, true, 0>(c, a, t) : launch_fir_k<D, R, NT, false, 0>(c, a, t);
 }
@@ -1051,7 +923,6 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
         for (int k = 0; k < 4; k++) a.rot[k] = make_float2(static_cast<float>(cos(k * rsum)), static_cast<float>(sin(k * rsum)));
         const double step = 4.0 * lp.shape.NT * rsum;
         a.rot_step = make_float2(static_cast<float>(cos(step)), static_cast<float>(sin(step)));
-        a.rot_stepw = make_float2(static_cast<float>(cos(128.0 * rsum)), static_cast<float>(sin(128.0 * rsum)));
         if (n_shift == 1 && ratios[0] != 0.0 && std::isnormal(ratios[0])) {
             int ex = 0;
             const double m = frexp(fabs(ratios[0]), &ex); // |ratio| = m * 2^ex, m in [0.5, 1)

@@ -145,7 +145,6 @@ struct Chain {
 
     // fused path (qd_fast.cu): segments are double buffered against H2D and D2H copies
     bool use_fast = true;
-    bool use_firw = true; // FAST cs8: the warp-private-tile variant of the fused kernel (option "use_firw")
     size_t segment_bytes = size_t(64) << 20; // raw bytes staged per segment for host / file sources
     bool pipeline_ready = false;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
