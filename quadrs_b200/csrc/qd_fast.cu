@@ -55,6 +55,7 @@ struct FirArgs {
     // FAST mode NCO: all leading shifts merged into one rotation of ratio_sum per sample
     float2 rot[4];    // e^{i k ratio_sum}, k = 0..3 (k = 0 unused)
     float2 rot_step;  // e^{i 4*NT ratio_sum}: from one group of a thread to its next
+    float rot2c;      // 2 cos(ratio_sum)
     // lean cs8 path (one shift): |ratio[0]| = rmant * 2^rexp exactly, rsign = +-1 (0: ratio is zero)
     uint64_t rmant;
     int rexp;
@@ -451,8 +452,7 @@ __device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr,
     }
     const float2 negk = make_float2(-8388736.0f, -8388736.0f); // -(2^23 + 128)
     const float2 r1c = make_float2(a.rot[1].x, a.rot[1].x), r1s = make_float2(a.rot[1].y, a.rot[1].y);
-    const float2 r2c = make_float2(a.rot[2].x, a.rot[2].x), r2s = make_float2(a.rot[2].y, a.rot[2].y);
-    const float2 r3c = make_float2(a.rot[3].x, a.rot[3].x), r3s = make_float2(a.rot[3].y, a.rot[3].y);
+    const float2 k2c = make_float2(a.rot2c, a.rot2c); // 2 cos(ratio)
     const float2 rsc = make_float2(rstep.x, rstep.x), rss = make_float2(rstep.y, rstep.y);
 #pragma unroll 2
     for (; rp < rp_end; rp += 8u * STRIDE, xb += STRIDE / Gm::G) {
@@ -469,8 +469,9 @@ __device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr,
             float2 ph[4];
             ph[0] = g;
             ph[1] = fma2(gp, r1s, mul2(g, r1c));
-            ph[2] = fma2(gp, r2s, mul2(g, r2c));
-            ph[3] = fma2(gp, r3s, mul2(g, r3c));
+            // e^{i(n+1)w} = 2 cos w e^{inw} - e^{i(n-1)w}: one packed FMA each, two steps from exact anchors
+            ph[2] = fma2(ph[1], k2c, make_float2(-g.x, -g.y));
+            ph[3] = fma2(ph[2], k2c, make_float2(-ph[1].x, -ph[1].y));
             float e[4];
             const uint32_t w0 = static_cast<uint32_t>(W >> 32);
 #pragma unroll
@@ -612,21 +613,30 @@ __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, 
     if (static_cast<uint32_t>(R * tid) < g.cnt) {
         // the unit's raw buffer ends at (unit_top0 + n_call)*D + L: later samples do not exist for
         // this read (filter.rs:68-71) and the ascending tap loop stops there
-        uint64_t unit_top0;
-        if (a.contiguous) {
-            // one division per tile (g.u0 = f0 / n_call); a thread's outputs start `rel` past that unit
-            uint64_t rel = g.f0 - g.u0 * a.n_call + static_cast<uint64_t>(R * tid);
-            uint64_t un = g.u0;
-            while (rel >= a.n_call) { // the tile runs over one or more unit boundaries
-                rel -= a.n_call;
-                un++;
-            }
-            unit_top0 = a.off0 + un * a.n_call;
+        int64_t s_lim; // samples from the thread's first one to the end of its unit's raw buffer
+        if (a.contiguous && a.ncall_log2 >= 0) {
+            // units tile the output stream and n_call is a power of two: the outputs left in the thread's unit
+            // come from a mask, and raw_end - n_first = left * D + (L - i0)
+            const uint64_t q = g.f0 + static_cast<uint64_t>(R * tid);
+            const uint64_t left = a.n_call - (q & (a.n_call - 1));
+            s_lim = static_cast<int64_t>(left * D + (a.L - (a.L - a.L / 2)));
         } else {
-            unit_top0 = a.off0 + g.unit * a.S;
+            uint64_t unit_top0;
+            if (a.contiguous) {
+                // one division per tile (g.u0 = f0 / n_call); a thread's outputs start `rel` past that unit
+                uint64_t rel = g.f0 - g.u0 * a.n_call + static_cast<uint64_t>(R * tid);
+                uint64_t un = g.u0;
+                while (rel >= a.n_call) { // the tile runs over one or more unit boundaries
+                    rel -= a.n_call;
+                    un++;
+                }
+                unit_top0 = a.off0 + un * a.n_call;
+            } else {
+                unit_top0 = a.off0 + g.unit * a.S;
+            }
+            const uint64_t raw_end = (unit_top0 + a.n_call) * D + a.L;
+            s_lim = static_cast<int64_t>(raw_end - g.n_tile0) - static_cast<int64_t>(tid) * (D * R);
         }
-        const uint64_t raw_end = (unit_top0 + a.n_call) * D + a.L;
-        const int64_t s_lim = static_cast<int64_t>(raw_end - g.n_tile0) - static_cast<int64_t>(tid) * (D * R);
         const int L = LS > 0 ? LS : static_cast<int>(a.L);
         const int s_total = (R - 1) * D + L;
         const int Q = (L + D - 1) / D, Lrem = L - (Q - 1) * D;
@@ -923,6 +933,7 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
         for (int k = 0; k < 4; k++) a.rot[k] = make_float2(static_cast<float>(cos(k * rsum)), static_cast<float>(sin(k * rsum)));
         const double step = 4.0 * lp.shape.NT * rsum;
         a.rot_step = make_float2(static_cast<float>(cos(step)), static_cast<float>(sin(step)));
+        a.rot2c = static_cast<float>(2.0 * cos(rsum));
         if (n_shift == 1 && ratios[0] != 0.0 && std::isnormal(ratios[0])) {
             int ex = 0;
             const double m = frexp(fabs(ratios[0]), &ex); // |ratio| = m * 2^ex, m in [0.5, 1)
