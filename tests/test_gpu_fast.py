@@ -252,6 +252,59 @@ def test_fast_mode_within_1e5_of_the_oracle(Q, fmt, rate, stages, base):
     assert worst <= 1e-5, worst
 
 
+def _lean_case(seed):
+    """cs8 FAST through the lean decode loop: random shift (sign, tiny, zero, near Nyquist), decimation, filter
+    length and capture offset, including offsets above 2^32 (more than 32 product bits rounded away) and offsets
+    placed so that a tile straddles a binade of n*ratio (where the number of rounded bits changes)."""
+    import math
+
+    rng = np.random.default_rng(0xFA57 + seed)
+    rate = int(rng.choice([2_400_000, 20_000_000, 100_000_000]))
+    kind = seed % 6
+    if kind == 0:
+        f = int(rng.integers(-rate // 2 + 1, rate // 2 - 1))
+    elif kind == 1:
+        f = int(rng.choice([-1, 1])) * (rate // 2 - 1)
+    elif kind == 2:
+        f = int(rng.choice([-3, 1, 7]))
+    elif kind == 3:
+        f = 0
+    else:
+        f = int(rng.integers(-rate // 2 + 1, rate // 2 - 1))
+    D = int(rng.choice([4, 8, 8, 32]))
+    L = int(rng.choice([40, 40, 40, 24, 64]))
+    stages = [("shift", f), ("lowpass", int(rng.integers(rate // 64, rate // 8)), D, L)]
+    if seed % 7 == 3:
+        stages = stages[1:]  # no shift at all: decode only
+    unit = 0x1000 * D
+    if kind == 4 and f != 0:  # straddle: bitlen(n * M) changes at n = 2^j / m, |ratio| = m * 2^ex
+        m, _ = math.frexp(abs(2.0 * math.pi * f / rate))
+        j = int(rng.integers(24, 36))
+        edge = int((1 << j) / m)
+        base = max(0, (edge - 3 * unit) // unit * unit)
+    elif kind == 5:
+        base = int(rng.integers(2**32, 2**36)) // unit * unit
+    else:
+        base = int(rng.integers(0, 2**31)) // unit * unit
+    return rate, stages, base
+
+
+@pytest.mark.parametrize("seed", range(36))
+def test_fast_cs8_lean_loop_random(Q, seed):
+    rate, stages, base = _lean_case(seed)
+    n = 0x1000 * _mult(stages) * 9 + 4096
+    total = base + n
+    raw, _ = synth_raw(O.CS8, n, first=base, rate=rate)
+    fast = gpu_chain(raw, O.CS8, rate, stages, base, total if base else 0, precision=Q.FAST)
+    first = base // (0x1000 * _mult(stages))
+    with kept_only():
+        want, _ = oracle_chain(raw, O.CS8, rate, stages, base, total if base else 0).write_mem(first_chunk=first, max_chunks=8)
+    got, _ = fast.write_mem(first_chunk=first, max_chunks=8)
+    assert len(got) == len(want) == 8 * 0x1000
+    worst = max(rel_err(got[c : c + 0x1000], want[c : c + 0x1000]) for c in range(0, len(want), 0x1000))
+    assert worst <= 1e-5, (worst, rate, stages, base)
+
+
 def _mult(stages):
     m = 1
     for st in stages:
