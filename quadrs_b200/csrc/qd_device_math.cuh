@@ -132,6 +132,37 @@ __device__ __forceinline__ float2 phasor_exact(uint64_t n, double ratio, const d
     return make_float2(static_cast<float>(c), static_cast<float>(s));
 }
 
+// ---- packed f32x2 arithmetic (sm_100: FFMA2 / FMUL2 / FADD2), each half an individually rounded IEEE op
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
+__device__ __forceinline__ float2 mul2(float2 a, float2 b)
+{
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b)
+{
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
 // buf[i] *= mul  (num-complex 0.4.6 MulAssign): re' = re*c - im*s ; im' = im*c + re*s
 __device__ __forceinline__ float2 cmul_exact(float2 a, float2 m)
 {

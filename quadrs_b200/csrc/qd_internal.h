@@ -233,6 +233,8 @@ struct FftArgs {
     // without the square root when magnitudes are not requested
     int use_thr;
     double thr[9];
+    uint32_t thr_hi[9];   // their high words: s >= thr decides on the high word alone unless the two are equal
+    float2 one;           // (1, 1), opaque to ptxas (see qd_stft.cu pmul_tw)
 };
 // thr[c], c = 0..6: smallest s = fl64(re^2 + im^2) whose glyph index is >= c + 1; thr[7]: start of the
 // graph[7] panic zone; thr[8]: smallest s with norm >= max.  false when min/max make that ill-defined.

@@ -14,6 +14,7 @@
 //   * the last pass feeds the epilogue from registers: fftshifted bin, glyph index by comparing
 //     fl64(re^2 + im^2) with per-glyph thresholds (no square root), magnitudes only when asked for.
 #include <algorithm>
+#include <cstring>
 
 #include "qd_device_math.cuh"
 #include "qd_internal.h"
@@ -60,62 +61,83 @@ __device__ __forceinline__ void load_group(const FftArgs &a, uint64_t u, uint32_
     }
 }
 
+
+// ---- the FFT's complex arithmetic on packed (re, im) pairs.  Every half is the same individually rounded
+// operation the scalar form in qd_device_math.cuh performs (a - b = a + (-b) exactly; the product pairs are
+// summed through an FMA by an opaque 1.0 so that ptxas cannot contract a multiply into the add).
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return add2(a, b); }
+__device__ __forceinline__ float2 psub(float2 a, float2 b) { return fma2(b, make_float2(-1.0f, -1.0f), a); }
+__device__ __forceinline__ float2 pmul_tw(float2 a, float2 w, float2 one)
+{
+    const float2 p1 = mul2(make_float2(a.x, a.x), w);                      // (ax wx, ax wy)
+    const float2 p2 = mul2(make_float2(a.y, a.y), make_float2(-w.y, w.x)); // (-ay wy, ay wx)
+    return fma2(p2, one, p1);
+}
+__device__ __forceinline__ void pradix4(float2 &t0, float2 &t1, float2 &t2, float2 &t3)
+{
+    const float2 s0 = padd(t0, t2), s1 = psub(t0, t2), s2 = padd(t1, t3), s3 = psub(t1, t3);
+    t0 = padd(s0, s2);
+    t1 = padd(s1, make_float2(s3.y, -s3.x)); // s1 - i*s3
+    t2 = psub(s0, s2);
+    t3 = padd(s1, make_float2(-s3.y, s3.x)); // s1 + i*s3
+}
+
 // two radix-4 levels on 16 points held by one thread: element i sits at position k + q*i of its block;
 // level 1 has sub-size q (twiddle index k), level 2 sub-size 4q (twiddle index k + q*c)
-__device__ __forceinline__ void levels2(float2 (&e)[16], uint32_t k, uint32_t q, uint32_t W, const float2 *__restrict__ T)
+__device__ __forceinline__ void levels2(float2 (&e)[16], uint32_t k, uint32_t q, uint32_t W, const float2 *__restrict__ T, float2 one)
 {
     if (k != 0) {
         const uint32_t sc = W / (4 * q);
         const float2 w1 = __ldg(T + k * sc), w2 = __ldg(T + 2 * k * sc), w3 = __ldg(T + 3 * k * sc);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            e[4 * j + 1] = cmul_tw(e[4 * j + 1], w1);
-            e[4 * j + 2] = cmul_tw(e[4 * j + 2], w2);
-            e[4 * j + 3] = cmul_tw(e[4 * j + 3], w3);
+            e[4 * j + 1] = pmul_tw(e[4 * j + 1], w1, one);
+            e[4 * j + 2] = pmul_tw(e[4 * j + 2], w2, one);
+            e[4 * j + 3] = pmul_tw(e[4 * j + 3], w3, one);
         }
     }
 #pragma unroll
-    for (int j = 0; j < 4; j++) radix4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
+    for (int j = 0; j < 4; j++) pradix4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
     const uint32_t sc2 = W / (16 * q);
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const uint32_t kp = k + q * c;
         if (kp != 0) {
-            e[c + 4] = cmul_tw(e[c + 4], __ldg(T + kp * sc2));
-            e[c + 8] = cmul_tw(e[c + 8], __ldg(T + 2 * kp * sc2));
-            e[c + 12] = cmul_tw(e[c + 12], __ldg(T + 3 * kp * sc2));
+            e[c + 4] = pmul_tw(e[c + 4], __ldg(T + kp * sc2), one);
+            e[c + 8] = pmul_tw(e[c + 8], __ldg(T + 2 * kp * sc2), one);
+            e[c + 12] = pmul_tw(e[c + 12], __ldg(T + 3 * kp * sc2), one);
         }
-        radix4(e[c], e[c + 4], e[c + 8], e[c + 12]);
+        pradix4(e[c], e[c + 4], e[c + 8], e[c + 12]);
     }
 }
 
 // one radix-4 level on 4 points: element i at position k + q*i, sub-size q
-__device__ __forceinline__ void levels1(float2 (&e)[4], uint32_t k, uint32_t q, uint32_t W, const float2 *__restrict__ T)
+__device__ __forceinline__ void levels1(float2 (&e)[4], uint32_t k, uint32_t q, uint32_t W, const float2 *__restrict__ T, float2 one)
 {
     if (k != 0) {
         const uint32_t sc = W / (4 * q);
-        e[1] = cmul_tw(e[1], __ldg(T + k * sc));
-        e[2] = cmul_tw(e[2], __ldg(T + 2 * k * sc));
-        e[3] = cmul_tw(e[3], __ldg(T + 3 * k * sc));
+        e[1] = pmul_tw(e[1], __ldg(T + k * sc), one);
+        e[2] = pmul_tw(e[2], __ldg(T + 2 * k * sc), one);
+        e[3] = pmul_tw(e[3], __ldg(T + 3 * k * sc), one);
     }
-    radix4(e[0], e[1], e[2], e[3]);
+    pradix4(e[0], e[1], e[2], e[3]);
 }
 
 // radix-2 innermost level and the first radix-4 level (sub-size 2) on 8 points, log2 W odd
-__device__ __forceinline__ void first_odd8(float2 (&e)[8], uint32_t W, const float2 *__restrict__ T)
+__device__ __forceinline__ void first_odd8(float2 (&e)[8], uint32_t W, const float2 *__restrict__ T, float2 one)
 {
 #pragma unroll
     for (int a = 0; a < 4; a++) {
         const float2 p = e[2 * a], q = e[2 * a + 1];
-        e[2 * a] = cadd(p, q);
-        e[2 * a + 1] = csub(p, q);
+        e[2 * a] = padd(p, q);
+        e[2 * a + 1] = psub(p, q);
     }
-    radix4(e[0], e[2], e[4], e[6]); // k = 0
+    pradix4(e[0], e[2], e[4], e[6]); // k = 0
     const uint32_t sc = W / 8;      // k = 1: w(8, c)
-    e[3] = cmul_tw(e[3], __ldg(T + sc));
-    e[5] = cmul_tw(e[5], __ldg(T + 2 * sc));
-    e[7] = cmul_tw(e[7], __ldg(T + 3 * sc));
-    radix4(e[1], e[3], e[5], e[7]);
+    e[3] = pmul_tw(e[3], __ldg(T + sc), one);
+    e[5] = pmul_tw(e[5], __ldg(T + 2 * sc), one);
+    e[7] = pmul_tw(e[7], __ldg(T + 3 * sc), one);
+    pradix4(e[1], e[3], e[5], e[7]);
 }
 
 // glyph index (and optional magnitude) of one output bin, fft.rs:48-60
@@ -179,7 +201,7 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
                 float2 e[8];
                 // sample i = r_m + 4*b of the stride-NG comb  ->  leaf offset b + 2*r_m
                 load_group<8>(a, u, t2, NG, e, [](int i) { return (i >> 2) | ((i & 3) << 1); });
-                first_odd8(e, W, T);
+                first_odd8(e, W, T, a.one);
                 if (REST == 0) {
 #pragma unroll
                     for (int i = 0; i < 8; i++) emit_bin(a, u, W, i, e[i]);
@@ -195,7 +217,7 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
             float2 e[16];
             // sample i = r_{m-1} + 4*r_m of the stride-TW comb  ->  leaf offset r_m + 4*r_{m-1}
             load_group<16>(a, u, lt, TW, e, [](int i) { return (i >> 2) | ((i & 3) << 2); });
-            levels2(e, 0, 1, W, T);
+            levels2(e, 0, 1, W, T, a.one);
             if constexpr (REST == 0) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) emit_bin(a, u, W, i, e[i]);
@@ -210,15 +232,15 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
             float2 e[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) e[i] = load_elem(a, u, i);
-            radix4(e[0], e[1], e[2], e[3]);
+            pradix4(e[0], e[1], e[2], e[3]);
 #pragma unroll
             for (int i = 0; i < 4; i++) emit_bin(a, u, W, i, e[i]);
         }
     } else if constexpr (LOGW == 1) {
         if (active) {
             const float2 p = load_elem(a, u, 0), q = load_elem(a, u, 1);
-            emit_bin(a, u, W, 0, cadd(p, q));
-            emit_bin(a, u, W, 1, csub(p, q));
+            emit_bin(a, u, W, 0, padd(p, q));
+            emit_bin(a, u, W, 1, psub(p, q));
         }
     } else if constexpr (LOGW == 0) {
         if (active) emit_bin(a, u, W, 0, load_elem(a, u, 0));
@@ -237,7 +259,7 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
             float2 e[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) e[i] = x[pad_idx(base + q * i)];
-            levels2(e, k, q, W, T);
+            levels2(e, k, q, W, T, a.one);
             if (last) {
 #pragma unroll
                 for (int i = 0; i < 16; i++) emit_bin(a, u, W, base + q * i, e[i]);
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
                 float2 e[4];
 #pragma unroll
                 for (int i = 0; i < 4; i++) e[i] = x[pad_idx(base + q * i)];
-                levels1(e, k, q, W, T);
+                levels1(e, k, q, W, T, a.one);
 #pragma unroll
                 for (int i = 0; i < 4; i++) emit_bin(a, u, W, base + q * i, e[i]);
             }
@@ -291,6 +313,12 @@ int launch_stft_fast(Chain &c, const FftArgs &fa_in, uint64_t units, bool *handl
     FftArgs fa = fa_in;
     fa.n_units = units;
     fa.use_thr = spark_thresholds(fa.mn, fa.mx, fa.thr) ? 1 : 0;
+    for (int i = 0; i < 9; i++) {
+        uint64_t bits;
+        memcpy(&bits, &fa.thr[i], 8);
+        fa.thr_hi[i] = static_cast<uint32_t>(bits >> 32);
+    }
+    fa.one = make_float2(1.0f, 1.0f);
     int logw = 0;
     while ((1u << logw) < fa.W) logw++;
     *handled = true;
