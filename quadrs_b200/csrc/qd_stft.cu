@@ -140,7 +140,45 @@ __device__ __forceinline__ void first_odd8(float2 (&e)[8], uint32_t W, const flo
     pradix4(e[1], e[3], e[5], e[7]);
 }
 
-// glyph index (and optional magnitude) of one output bin, fft.rs:48-60
+// glyph index of one bin from the thresholds on s = fl64(re^2 + im^2) (spark_thresholds), every case
+__device__ __noinline__ int glyph_by_threshold(const FftArgs &a, float2 v)
+{
+    const double x = v.x, y = v.y;
+    double s = fma(x, x, __dmul_rn(y, y)); // = fl64(x^2 + y^2): both squares are exact in f64
+    if (s != s) { // NaN in, or inf - inf: hypotf gives inf if either part is infinite, else NaN
+        if (isinf(v.x) || isinf(v.y)) s = __longlong_as_double(0x7ff0000000000000ll);
+        else return glyph_index(__int_as_float(0x7fc00000), a.mn, a.mx, a.distinction);
+    }
+    // r = #{c < 7 : s >= thr[c]} by bisection (thr is non-decreasing; NaN entries never compare true)
+    const bool h3 = s >= a.thr[3];
+    const bool h1 = s >= (h3 ? a.thr[5] : a.thr[1]);
+    const double t0 = h3 ? (h1 ? a.thr[6] : a.thr[4]) : (h1 ? a.thr[2] : a.thr[0]);
+    const int r = (h3 ? 4 : 0) + (h1 ? 2 : 0) + (s >= t0 ? 1 : 0);
+    return s >= a.thr[8] ? 8 : (s >= a.thr[7] ? 9 : r);
+}
+
+// The same decisions on the HIGH WORD of s alone: for finite s >= 0 and a threshold t >= 0 (or NaN),
+// s >= t  <=>  hi(s) >= hi(t) unless the two high words are equal.  Any compared threshold whose high word
+// equals hi(s), and every non-finite s, goes through the full comparison above.
+__device__ __forceinline__ int glyph_fast(const FftArgs &a, float2 v)
+{
+    const double x = v.x, y = v.y;
+    const double s = fma(x, x, __dmul_rn(y, y));
+    const uint32_t sh = static_cast<uint32_t>(__double2hiint(s));
+    const uint32_t c3 = a.thr_hi[3];
+    const bool h3 = sh >= c3;
+    const uint32_t c1 = h3 ? a.thr_hi[5] : a.thr_hi[1];
+    const bool h1 = sh >= c1;
+    const uint32_t c0 = h3 ? (h1 ? a.thr_hi[6] : a.thr_hi[4]) : (h1 ? a.thr_hi[2] : a.thr_hi[0]);
+    const int r = (h3 ? 4 : 0) + (h1 ? 2 : 0) + (sh >= c0 ? 1 : 0);
+    const uint32_t c8 = a.thr_hi[8], c7 = a.thr_hi[7];
+    int g = sh >= c8 ? 8 : (sh >= c7 ? 9 : r);
+    if (sh == c3 || sh == c1 || sh == c0 || sh == c8 || sh == c7 || sh >= 0x7ff00000u) g = glyph_by_threshold(a, v);
+    if (g == 9) *a.panic_flag = 1;
+    return g;
+}
+
+// glyph index (and optional magnitude) of one output bin, fft.rs:48-60: the general form
 __device__ __forceinline__ void emit_bin(const FftArgs &a, uint64_t u, uint32_t W, uint32_t pos, float2 v)
 {
     const uint32_t b = W > 1 ? ((pos + W / 2) & (W - 1)) : 0; // display order: bins W/2..W-1 then 0..W/2-1
@@ -150,24 +188,40 @@ __device__ __forceinline__ void emit_bin(const FftArgs &a, uint64_t u, uint32_t 
         const float norm = hypot_exact(v.x, v.y);
         if (a.mag) a.mag[o] = norm;
         g = glyph_index(norm, a.mn, a.mx, a.distinction);
+        if (g == 9) *a.panic_flag = 1;
     } else {
-        const double x = v.x, y = v.y;
-        double s = fma(x, x, __dmul_rn(y, y)); // = fl64(x^2 + y^2): both squares are exact in f64
-        bool nan1 = false;
-        if (s != s) { // NaN in, or inf - inf: hypotf gives inf if either part is infinite, else NaN
-            if (isinf(v.x) || isinf(v.y)) s = __longlong_as_double(0x7ff0000000000000ll);
-            else nan1 = true;
-        }
-        // r = #{c < 7 : s >= thr[c]} by bisection (thr is non-decreasing; NaN entries never compare true)
-        const bool h3 = s >= a.thr[3];
-        const bool h1 = s >= (h3 ? a.thr[5] : a.thr[1]);
-        const double t0 = h3 ? (h1 ? a.thr[6] : a.thr[4]) : (h1 ? a.thr[2] : a.thr[0]);
-        const int r = (h3 ? 4 : 0) + (h1 ? 2 : 0) + (s >= t0 ? 1 : 0);
-        g = s >= a.thr[8] ? 8 : (s >= a.thr[7] ? 9 : r);
-        if (nan1) g = glyph_index(__int_as_float(0x7fc00000), a.mn, a.mx, a.distinction);
+        g = glyph_fast(a, v);
     }
-    if (g == 9) *a.panic_flag = 1;
     a.idx[o] = static_cast<uint8_t>(g);
+}
+
+// A whole window of N <= 16 bins held by one thread (element i is FFT bin i): glyphs packed into words
+template <int N>
+__device__ __forceinline__ void emit_window(const FftArgs &a, uint64_t u, const float2 *e)
+{
+    if (N < 4 || a.mag || !a.use_thr || (reinterpret_cast<uintptr_t>(a.idx) & 3)) {
+#pragma unroll
+        for (int i = 0; i < N; i++) emit_bin(a, u, N, i, e[i]);
+        return;
+    }
+    uint32_t w[N >= 4 ? N / 4 : 1];
+#pragma unroll
+    for (int j = 0; j < N / 4; j++) w[j] = 0;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        const int b = (i + N / 2) & (N - 1);
+        w[b / 4] |= static_cast<uint32_t>(glyph_fast(a, e[i])) << (8 * (b & 3));
+    }
+    uint32_t *o = reinterpret_cast<uint32_t *>(a.idx + static_cast<size_t>(u) * N);
+#pragma unroll
+    for (int j = 0; j < N / 4; j++) o[j] = w[j];
+}
+
+// 16 bins of a wider window: staged as bytes in the team's row of shared memory (gl), written out by
+// store_row once the whole row is there
+__device__ __forceinline__ void stage_bin(const FftArgs &a, uint8_t *gl, uint32_t W, uint32_t pos, float2 v)
+{
+    gl[(pos + W / 2) & (W - 1)] = static_cast<uint8_t>(glyph_fast(a, v));
 }
 
 template <int LOGW>
@@ -182,12 +236,15 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
     constexpr int REST = LOGW - FIRST_BITS;                // log2 of what the later passes still combine
     constexpr int N16 = REST / 4, N4 = (REST % 4) / 2;
     constexpr uint32_t WIN_SMEM = pad_idx(W) + 1;
-    extern __shared__ float2 stft_smem[];
+    constexpr uint32_t X_ELEMS = (WPC * WIN_SMEM + 1) & ~1u; // float2 elements, so the glyph rows start 16-byte aligned
+    extern __shared__ __align__(16) float2 stft_smem[];
 
     const uint32_t team = threadIdx.x / TW, lt = threadIdx.x % TW;
     const uint64_t u = static_cast<uint64_t>(blockIdx.x) * WPC + team;
     const bool active = u < a.n_units;
     float2 *x = stft_smem + static_cast<size_t>(team) * WIN_SMEM;
+    uint8_t *gl = reinterpret_cast<uint8_t *>(stft_smem + X_ELEMS) + static_cast<size_t>(team) * W; // the team's glyph row
+    const bool staged = !a.mag && a.use_thr; // index-only output: rows leave through shared memory, 16 bytes per thread
     const float2 *__restrict__ T = a.tw;
 
     // ---------------- pass 1: global -> registers -> first levels ----------------
@@ -203,8 +260,7 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
                 load_group<8>(a, u, t2, NG, e, [](int i) { return (i >> 2) | ((i & 3) << 1); });
                 first_odd8(e, W, T, a.one);
                 if (REST == 0) {
-#pragma unroll
-                    for (int i = 0; i < 8; i++) emit_bin(a, u, W, i, e[i]);
+                    emit_window<8>(a, u, e);
                 } else {
                     const uint32_t g = digitrev4(t2, M - 1);
 #pragma unroll
@@ -219,8 +275,7 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
             load_group<16>(a, u, lt, TW, e, [](int i) { return (i >> 2) | ((i & 3) << 2); });
             levels2(e, 0, 1, W, T, a.one);
             if constexpr (REST == 0) {
-#pragma unroll
-                for (int i = 0; i < 16; i++) emit_bin(a, u, W, i, e[i]);
+                emit_window<16>(a, u, e);
             } else {
                 const uint32_t g = digitrev4(lt, M - 2);
 #pragma unroll
@@ -233,8 +288,7 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 4; i++) e[i] = load_elem(a, u, i);
             pradix4(e[0], e[1], e[2], e[3]);
-#pragma unroll
-            for (int i = 0; i < 4; i++) emit_bin(a, u, W, i, e[i]);
+            emit_window<4>(a, u, e);
         }
     } else if constexpr (LOGW == 1) {
         if (active) {
@@ -261,8 +315,13 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
             for (int i = 0; i < 16; i++) e[i] = x[pad_idx(base + q * i)];
             levels2(e, k, q, W, T, a.one);
             if (last) {
+                if (staged) {
 #pragma unroll
-                for (int i = 0; i < 16; i++) emit_bin(a, u, W, base + q * i, e[i]);
+                    for (int i = 0; i < 16; i++) stage_bin(a, gl, W, base + q * i, e[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; i++) emit_bin(a, u, W, base + q * i, e[i]);
+                }
             } else {
 #pragma unroll
                 for (int i = 0; i < 16; i++) x[pad_idx(base + q * i)] = e[i];
@@ -282,8 +341,27 @@ __global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 4; i++) e[i] = x[pad_idx(base + q * i)];
                 levels1(e, k, q, W, T, a.one);
+                if (staged) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) emit_bin(a, u, W, base + q * i, e[i]);
+                    for (int i = 0; i < 4; i++) stage_bin(a, gl, W, base + q * i, e[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) emit_bin(a, u, W, base + q * i, e[i]);
+                }
+            }
+        }
+    }
+    if (staged) { // every thread of the team carries 16 consecutive bytes of its window's row out
+        __syncthreads();
+        if (active) {
+            const uint4 row = *reinterpret_cast<const uint4 *>(gl + 16 * lt);
+            uint8_t *o = a.idx + static_cast<size_t>(u) * W + 16 * lt;
+            if ((reinterpret_cast<uintptr_t>(a.idx) & 15) == 0) {
+                *reinterpret_cast<uint4 *>(o) = row;
+            } else {
+                const uint32_t wd[4] = {row.x, row.y, row.z, row.w};
+#pragma unroll
+                for (int i = 0; i < 16; i++) o[i] = static_cast<uint8_t>(wd[i / 4] >> (8 * (i & 3)));
             }
         }
     }
@@ -296,7 +374,7 @@ static int launch_stft_k(Chain &c, const FftArgs &fa, uint64_t units)
     constexpr uint32_t TW = W >= 16 ? W / 16 : 1;
     constexpr uint32_t WPC = kStftThreads / TW;
     constexpr int FIRST_BITS = (LOGW & 1) ? (LOGW >= 3 ? 3 : 1) : (LOGW >= 4 ? 4 : LOGW);
-    const size_t smem = LOGW == FIRST_BITS ? 0 : static_cast<size_t>(WPC) * (pad_idx(W) + 1) * sizeof(float2);
+    const size_t smem = LOGW == FIRST_BITS ? 0 : static_cast<size_t>((WPC * (pad_idx(W) + 1) + 1) & ~1u) * sizeof(float2) + static_cast<size_t>(WPC) * W;
     if (smem > 48 * 1024)
         QD_CUDA(cudaFuncSetAttribute(fk_stft<LOGW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const uint64_t grid = (units + WPC - 1) / WPC;
