@@ -225,7 +225,7 @@ __device__ __forceinline__ void stage_bin(const FftArgs &a, uint8_t *gl, uint32_
 }
 
 template <int LOGW>
-__global__ void __launch_bounds__(kStftThreads) fk_stft(const __grid_constant__ FftArgs a)
+__global__ void __launch_bounds__(kStftThreads, 4) fk_stft(const __grid_constant__ FftArgs a)
 {
     constexpr uint32_t W = 1u << LOGW;
     constexpr int M = LOGW / 2;
