@@ -78,6 +78,7 @@ def parse_args():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--samples", type=int, default=0, help="samples per GPU (default: the workload's)")
     ap.add_argument("--precision", default="auto", choices=["auto", "exact", "fast"])
+    ap.add_argument("--segment-mb", type=int, default=0, help="host-path segment size in MiB (default: the library's)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -306,7 +307,10 @@ def run_b200(args, w):
         s = src
         for st in w["stages"]:
             s = s.shift(st[1]) if st[0] == "shift" else s.lowpass(st[1], st[2], st[3])
-        return s.with_precision(precision if prec is None else prec).with_stream(stream.cuda_stream)
+        s = s.with_precision(precision if prec is None else prec).with_stream(stream.cuda_stream)
+        if args.segment_mb:
+            s.set_option("segment_bytes", args.segment_mb << 20)
+        return s
 
     dev_chain = build_chain(Q.Samples.from_device(d_in.data_ptr(), n_in * pb, fmt, rate, local,
                                                   base_sample=plan.first_sample, total_samples=total, keep=(d_in,)))
