@@ -391,7 +391,7 @@ __device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr,
     const float2 r1c = make_float2(a.rot[1].x, a.rot[1].x), r1s = make_float2(a.rot[1].y, a.rot[1].y);
     const float2 k2c = make_float2(a.rot2c, a.rot2c); // 2 cos(ratio)
     const float2 rsc = make_float2(rstep.x, rstep.x), rss = make_float2(rstep.y, rstep.y);
-#pragma unroll 2
+#pragma unroll 4
     for (; rp < rp_end; rp += 8u * STRIDE, xb += STRIDE / Gm::G) {
         uint2 v;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(rp));
