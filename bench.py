@@ -102,6 +102,28 @@ def make_oracle_synth(O, w):
 # ------------------------------------------------------------------------------------------------
 # clocks sampling during the timed region
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_cpus(gpu_index: int):
+    """Run this rank on the CPUs NVML reports as local to its GPU, so that the pinned host buffers of the e2e
+    path are allocated on that NUMA node (what a deployment does with numactl).  Returns the CPU count or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu_index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (NVML, ~1 ms period, from a thread:
     ctypes releases the GIL while the library call runs).  Falls back to nvidia-smi -lms when NVML is missing."""
@@ -269,6 +291,7 @@ def run_b200(args, w):
         raise SystemExit("bench.py: no CUDA device; quadrs_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = bind_to_gpu_cpus(local)  # pinned host buffers (e2e) are first-touched on the GPU's NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -455,7 +478,8 @@ def run_b200(args, w):
                        "capture_samples": total, "units_per_gpu": n_units, "input_bytes_per_gpu": n_in * pb,
                        "precision": "fast" if precision == Q.FAST else "exact",
                        "l2": "inputs larger than L2 (no flush needed)" if n_in * pb > 256 * 2**20 else "input smaller than 2x L2",
-                       "sharding": f"{world} contiguous unit ranges with halo, absolute indices, no collective"},
+                       "sharding": f"{world} contiguous unit ranges with halo, absolute indices, no collective",
+                       "rank_cpu_affinity": affinity},
             "clocks": clocks,
             "gpu_launches": launches_all,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

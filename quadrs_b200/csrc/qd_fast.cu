@@ -61,7 +61,6 @@ struct FirArgs {
     int rexp;
     int rsign;
     int ncall_log2;   // n_call = 2^ncall_log2, or -1
-    double rot_tile[2]; // contiguous mode: e^{i dn ratio}, dn = raw samples from one tile of a CTA to its next
 };
 
 // Per-tile phase state of the lean FAST decode, computed by one thread while the previous tile is filtered
@@ -319,22 +318,17 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
 // the k bits the multiply rounds away.  Those bits are n * rmant mod 2^k: kept left-aligned in a 64-bit
 // integer they advance by one wrapping add per group, and their top word read as a signed fraction of an
 // ulp is the rounding error (ties excepted: they round to even, here always up).
-template <bool STEP>
 __device__ __forceinline__ void lean_phase(const FirArgs &a, uint64_t n0, uint32_t span, LeanPhase *ph)
 {
-    if (STEP) { // the CTA's previous tile lies a fixed distance back: one f64 rotation (a few hundred steps per launch)
-        const double c = ph->ac, s = ph->as, rc = a.rot_tile[0], rs = a.rot_tile[1];
-        ph->ac = fma(c, rc, -__dmul_rn(s, rs));
-        ph->as = fma(c, rs, __dmul_rn(s, rc));
-    } else {
-        const double nd = __ull2double_rn(n0), r = a.ratio[0];
-        const double p = __dmul_rn(nd, r);
-        const double e = fma(nd, r, -p); // exact product minus the rounded one
-        double c, s;
-        sincos_f64k(p, a.sincos, a.k, c, s);
-        ph->ac = fma(-e, s, c);
-        ph->as = fma(e, c, s);
-    }
+    // always from scratch (not stepped from the CTA's previous tile): a tile's result must not depend on which
+    // launch -- host-path segment, shard -- it is part of
+    const double nd = __ull2double_rn(n0), r = a.ratio[0];
+    const double p = __dmul_rn(nd, r);
+    const double e = fma(nd, r, -p); // exact product minus the rounded one
+    double c, s;
+    sincos_f64k(p, a.sincos, a.k, c, s);
+    ph->ac = fma(-e, s, c);
+    ph->as = fma(e, c, s);
     const uint64_t M = a.rmant;
     auto bitlen = [&](uint64_t n) {
         const uint64_t hi = __umul64hi(n, M), lo = n * M;
@@ -636,16 +630,14 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    auto tile_phase = [&](const TileGeo &g, bool first) { // thread 0, one tile ahead
-        const uint32_t span = static_cast<uint32_t>(g.cnt - 1) * D + a.L + 4;
-        if (a.contiguous && !first) lean_phase<true>(a, g.n_tile0, span, lphase);
-        else lean_phase<false>(a, g.n_tile0, span, lphase);
+    auto tile_phase = [&](const TileGeo &g) { // one spare lane, one tile ahead
+        lean_phase(a, g.n_tile0, static_cast<uint32_t>(g.cnt - 1) * D + a.L + 4, lphase);
     };
     if (lean_mix) {
         double c, s;
         sincos_f64k(__dmul_rn(static_cast<double>(4 * tid), a.ratio[0]), a.sincos, a.k, c, s);
         ttab[tid] = make_double2(c, s);
-        if (tid == 0 && blockIdx.x < a.n_tiles) tile_phase(tile_geo<D, Gm::T_OUT>(a, blockIdx.x), true);
+        if (tid == 0 && blockIdx.x < a.n_tiles) tile_phase(tile_geo<D, Gm::T_OUT>(a, blockIdx.x));
     }
     __syncthreads();
 
@@ -705,7 +697,7 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x));
         // the next tile's phase state: another warp's spare lane, so no warp carries both chores into the barrier
         if (lean_mix && tid == (NT > 32 ? 32 : 0) && tile + gridDim.x < a.n_tiles)
-            tile_phase(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x), false);
+            tile_phase(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x));
 
         // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
         fir_tile<D, R, NT, LMAX, EXACT, LS>(a, taps, g, X, tid, tid);
@@ -740,15 +732,7 @@ static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
     const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
     const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, ctas_per_sm<D, R, NT, EXACT, LS>())));
     QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    FirArgs b = a;
-    if (!EXACT && a.n_shift == 1) {
-        // exact angle of dn * ratio as p + e (the product's rounding error recovered by an FMA)
-        const double dn = static_cast<double>(static_cast<uint64_t>(grid) * Gm::T_OUT * D);
-        const double p = dn * a.ratio[0], e = fma(dn, a.ratio[0], -p);
-        b.rot_tile[0] = cos(p) - e * sin(p);
-        b.rot_tile[1] = sin(p) + e * cos(p);
-    }
-    fk_fir<D, R, NT, EXACT, LS><<<grid, NT, smem, c.stream>>>(b, t);
+    fk_fir<D, R, NT, EXACT, LS><<<grid, NT, smem, c.stream>>>(a, t);
     QD_LAUNCHED();
     return QD_OK;
 }
