@@ -305,6 +305,26 @@ def test_fast_cs8_lean_loop_random(Q, seed):
     assert worst <= 1e-5, (worst, rate, stages, base)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_fast_cs8_lean_loop_under_overlapping_windows(Q, seed):
+    """FAST through sparkfft: overlapping windows are separate reads (one unit each, their own truncated tails),
+    so the fused kernel runs in its per-unit tiling; magnitudes stay within 1e-5 of the oracle's (max-norm per row)."""
+    rate, stages, base = _lean_case(seed * 5 + 1)
+    W, S = [(64, 16), (128, 128), (32, 7), (256, 64)][seed % 4]
+    n = _mult(stages) * (W + 40 * S) + 4096
+    total = base + n
+    raw, _ = synth_raw(O.CS8, n, first=base, rate=rate)
+    fast = gpu_chain(raw, O.CS8, rate, stages, base, total if base else 0, precision=Q.FAST)
+    first = -(-base // (_mult(stages) * S))
+    rng = (1e-4, 1e4)
+    with kept_only():
+        _, want = oracle_chain(raw, O.CS8, rate, stages, base, total if base else 0).spark_fft(W, S, rng, first_row=first, max_rows=24)
+    _, got = fast.spark_fft(W, S, rng, first_row=first, max_rows=24, want_mag=True)
+    assert got.shape == want.shape and want.shape[0] == 24
+    worst = max(float(np.abs(got[r] - want[r]).max() / max(np.abs(want[r]).max(), 1e-30)) for r in range(24))
+    assert worst <= 1e-5, (worst, rate, stages, base, W, S)
+
+
 def _mult(stages):
     m = 1
     for st in stages:
