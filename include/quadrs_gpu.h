@@ -65,7 +65,9 @@ typedef enum {
 /* ---- sources: Operation::From / Operation::Gen, src/lib.rs:26-29,54-58,89-101 ---- */
 typedef enum {
     QD_SRC_HOST_MEM = 0,   /* raw capture bytes in host memory (what SampleFile preads, samples.rs:72-93) */
-    QD_SRC_DEVICE_MEM = 1, /* the same bytes already resident in HBM (pointer aligned to one sample) */
+    QD_SRC_DEVICE_MEM = 1, /* the same bytes already resident in HBM: pointer aligned to one sample, and the
+                              allocation readable up to the next 16-byte boundary past the last sample (tiles
+                              are fetched by 16-byte-granular bulk copies; any cudaMalloc block satisfies it) */
     QD_SRC_FILE = 2,       /* path; the library preads it */
     QD_SRC_GEN = 3         /* gen.rs */
 } qd_source_kind;
