@@ -426,6 +426,85 @@ __device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr,
     }
 }
 
+// ---------------------------------------------------------------------------- lean EXACT decode (integer formats)
+// The same loop structure for the bit-exact mode: one 4-sample group per thread and iteration, incremental
+// shared-memory addresses, integers made into floats by the mantissa trick (exact, like the conversion it
+// replaces), then exactly the reference's operations: the IEEE quotient (div_exact2), the offset subtraction,
+// fl64(n * ratio), an f64 sin/cos per sample and shift, and num-complex's multiply with every product and sum
+// rounded on its own (packed: (x c, x s) + (-y s, y c) through an FMA by the opaque 1.0).
+template <int FMT>
+__device__ __forceinline__ void unpack_group(uint32_t rp, float2 (&x)[4], float2 one)
+{
+    if (FMT == QD_FMT_CS16) {
+        uint4 v;
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(rp));
+        const uint32_t w[4] = {v.x ^ 0x80008000u, v.y ^ 0x80008000u, v.z ^ 0x80008000u, v.w ^ 0x80008000u};
+        const float2 negk = make_float2(-8421376.0f, -8421376.0f); // -(2^23 + 32768)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 n = add2(make_float2(__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7410)),
+                                              __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7432))), negk);
+            x[i] = fma2(div_exact2(n, 65535.0f, 1.0f / 65535.0f), one, make_float2(-32767.5f, -32767.5f)); // lib.rs:253
+        }
+    } else {
+        uint2 v;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(rp));
+        const uint32_t flip = FMT == QD_FMT_CS8 ? 0x80808080u : 0u;
+        const uint32_t w[2] = {v.x ^ flip, v.y ^ flip};
+        const float kk = FMT == QD_FMT_CS8 ? -8388736.0f : -8388608.0f; // -(2^23 + 128) or -2^23
+        const float2 negk = make_float2(kk, kk);
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t word = w[i >> 1];
+            const uint32_t sel = (i & 1) ? 0x7442 : 0x7440;
+            const float2 n = add2(make_float2(__uint_as_float(__byte_perm(word, 0x4B000000u, sel)),
+                                              __uint_as_float(__byte_perm(word, 0x4B000000u, sel + 1))), negk);
+            if (FMT == QD_FMT_CS8) x[i] = div_exact2(n, 127.0f, 1.0f / 127.0f); // lib.rs:251
+            else x[i] = fma2(div_exact2(n, 255.0f, 1.0f / 255.0f), one, make_float2(-127.5f, -127.5f)); // lib.rs:252
+        }
+    }
+}
+
+template <class Gm, int STRIDE, int FMT>
+__device__ __forceinline__ void decode_lean_exact(const FirArgs &a, uint32_t raw_addr, uint32_t n_dec, uint64_t n0,
+                                                  float4 *__restrict__ X4, int idx)
+{
+    static_assert(STRIDE % Gm::G == 0, "a thread's groups stay in one row");
+    constexpr uint32_t GB = FMT == QD_FMT_CS16 ? 16u : 8u; // bytes per group of 4 samples
+    const uint32_t n_loc = (n_dec + 3) >> 2;
+    uint32_t rp = raw_addr + GB * static_cast<uint32_t>(idx);
+    const uint32_t rp_end = raw_addr + GB * n_loc;
+    float4 *xb = X4 + (idx & (Gm::G - 1)) * Gm::PITCH + (idx >> Gm::LOG_G);
+    const float2 one = a.one;
+    const int n_shift = a.n_shift;
+    double nd = __ull2double_rn(n0 + static_cast<uint64_t>(4 * idx)); // absolute index of the group's first sample
+    for (; rp < rp_end; rp += GB * STRIDE, xb += STRIDE / Gm::G) {
+        float2 x[4];
+        unpack_group<FMT>(rp, x, one);
+        if (n_shift) {
+            auto mix = [&](float2 v, double ni, double ratio) {
+                double c, sn;
+                sincos_f64k(__dmul_rn(ni, ratio), a.sincos, a.k, c, sn); // shift.rs:49-50
+                const float cf = static_cast<float>(c), sf = static_cast<float>(sn);
+                const float2 p1 = mul2(make_float2(v.x, v.x), make_float2(cf, sf));
+                const float2 p2 = mul2(make_float2(v.y, v.y), make_float2(-sf, cf));
+                return fma2(p2, one, p1); // (x c - y s, x s + y c), shift.rs:51
+            };
+            const double r0 = a.ratio[0];
+#pragma unroll
+            for (int i = 0; i < 4; i++) x[i] = mix(x[i], __dadd_rn(nd, static_cast<double>(i)), r0); // four independent chains
+            for (int sft = 1; sft < n_shift; sft++) {
+                const double rs = a.ratio[sft];
+#pragma unroll
+                for (int i = 0; i < 4; i++) x[i] = mix(x[i], __dadd_rn(nd, static_cast<double>(i)), rs);
+            }
+            nd = __dadd_rn(nd, static_cast<double>(4 * STRIDE));
+        }
+        xb[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+        xb[Gm::G * Gm::PITCH] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+    }
+}
+
 template <int D, int R, int NT, int LMAX, bool MIX>
 __device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
                                                  uint64_t n_tile0, const LeanPhase *lp, const double2 *ttab,
@@ -676,6 +755,14 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
             if (!EXACT && lean && (lead & 3) == 0 && (!lean_mix || lphase->ok)) {
                 if (lean_mix) decode_tile_lean<D, R, NT, LMAX, true>(a, raw, lead, n_dec, g.n_tile0, lphase, ttab, X, tid);
                 else decode_tile_lean<D, R, NT, LMAX, false>(a, raw, lead, n_dec, g.n_tile0, lphase, ttab, X, tid);
+            } else if (EXACT && staged && (lead & 3) == 0) {
+                const uint32_t raw_addr = smem_u32(raw) + pb * lead;
+                float4 *X4 = reinterpret_cast<float4 *>(X);
+                switch (a.fmt) {
+                case QD_FMT_CS8: decode_lean_exact<Gm, NT, QD_FMT_CS8>(a, raw_addr, n_dec, g.n_tile0, X4, tid); break;
+                case QD_FMT_CU8: decode_lean_exact<Gm, NT, QD_FMT_CU8>(a, raw_addr, n_dec, g.n_tile0, X4, tid); break;
+                default: decode_lean_exact<Gm, NT, QD_FMT_CS16>(a, raw_addr, n_dec, g.n_tile0, X4, tid); break;
+                }
             } else if ((lead & 3) == 0) {
                 switch (a.fmt) {
                 case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
