@@ -679,7 +679,7 @@ template <int D, int R, int NT, bool EXACT, int LS>
 constexpr int ctas_per_sm()
 {
     if (NT <= 128 && D <= 8) {
-        if (!EXACT && LS > 0) return (R <= 2 ? 8 : 5) * (128 / NT);
+        if (LS > 0) return (R <= 2 ? 8 : 5) * (128 / NT);
         return 4 * (128 / NT);
     }
     return 2;
