@@ -102,10 +102,13 @@ inline SinCosK make_sincos_k()
 __device__ __forceinline__ void sincos_f64k(double theta, const double *__restrict__ tab, const SinCosK &k, double &cd,
                                             double &sd)
 {
-    const double kd = rint(__dmul_rn(theta, k.K));
+    // kd = rint(theta * K) and its low bits from one addition: 1.5 * 2^52 + p has ulp 1, so the add rounds p to the
+    // nearest-even integer (= rint; |p| < 2^43 here) and leaves that integer in the low mantissa bits
+    const double t = __dadd_rn(__dmul_rn(theta, k.K), 6755399441055744.0);
+    const double kd = __dadd_rn(t, -6755399441055744.0);
     double r = fma(-kd, k.C1, theta);
     r = fma(-kd, k.C2, r);
-    const int ki = static_cast<int>(static_cast<long long>(kd)) & 255;
+    const int ki = __double2loint(t) & 255;
     const double2 *tp = reinterpret_cast<const double2 *>(tab) + 2 * ki;
     const double2 tcos = __ldg(tp), tsin = __ldg(tp + 1); // {ch, cl}, {sh, sl}
     const double r2 = __dmul_rn(r, r);
