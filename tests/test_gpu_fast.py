@@ -271,7 +271,7 @@ def _lean_case(seed):
         f = 0
     else:
         f = int(rng.integers(-rate // 2 + 1, rate // 2 - 1))
-    D = int(rng.choice([4, 8, 8, 32]))
+    D = int(rng.choice([2, 4, 8, 8, 16, 32]))
     L = int(rng.choice([40, 40, 40, 24, 64]))
     stages = [("shift", f), ("lowpass", int(rng.integers(rate // 64, rate // 8)), D, L)]
     if seed % 7 == 3:
@@ -289,7 +289,7 @@ def _lean_case(seed):
     return rate, stages, base
 
 
-@pytest.mark.parametrize("seed", range(36))
+@pytest.mark.parametrize("seed", range(48))
 def test_fast_cs8_lean_loop_random(Q, seed):
     rate, stages, base = _lean_case(seed)
     n = 0x1000 * _mult(stages) * 9 + 4096
