@@ -42,7 +42,7 @@ WORKLOADS = {
         fmt=CS8, rate=20_000_000, samples=2**30,
         stages=[("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)], sink=("write", 0x1000),
         tones=[(1.6e6, 45, 0), (-4.1e6, 30, 0), (0.3e6, 20, 3000)], noise=6, seed=0x5EED0002,
-        out_bytes_per_unit=0x1000 * 8, cpu_units=1536, ref_units_per_thread=96),
+        out_bytes_per_unit=0x1000 * 8, cpu_units=8192, ref_units_per_thread=512),
     # BASELINE.json configs[3] (per-GPU shard of 2^30 samples by default; --samples overrides)
     "cfg4": dict(
         title="synthetic cs16 100 MS/s: shift 7000000 | lowpass -power 400 -decimate 16 2000000 | sparkfft -width 128 -range 0.5:50",
@@ -242,7 +242,7 @@ def run_reference(args, w):
         if st[0] == "lowpass":
             need = need * st[2] + st[3]
             mult *= st[2]
-    units = threads * w["ref_units_per_thread"]
+    units = min(threads * w["ref_units_per_thread"], 16384)  # bounded: at most 2^29 input samples per step for cfg2
     n_in = (units - 1) * stride * mult + need + 64
     raw = O.synth_fill(make_oracle_synth(O, w), w["fmt"], 0, n_in)
     sink = w["sink"]
