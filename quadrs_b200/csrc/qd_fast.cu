@@ -505,6 +505,46 @@ __device__ __forceinline__ void decode_lean_exact(const FirArgs &a, uint32_t raw
     }
 }
 
+// ---------------------------------------------------------------------------- cf32 without a shift: a plain copy
+// A cf32 sample's "decode" is a bit copy (lib.rs:248), so with no shift in front of the filter a group of four
+// samples goes from global memory to its two slots of the polyphase layout untouched.  With 8 bytes per sample
+// this path is bound by the bytes it has in flight: two groups (four 128-bit loads) per thread are issued
+// before the first store.
+template <class Gm, int STRIDE>
+__device__ __forceinline__ void decode_cf32_copy(const uint8_t *gsrc, uint32_t n_dec, float2 *__restrict__ X, int idx)
+{
+    static_assert(STRIDE % Gm::G == 0, "a thread's groups stay in one row");
+    constexpr int B = 2; // groups in flight per thread (three or four spill under the 96-register cap and measure slower)
+    const uint32_t n_full = n_dec >> 2;
+    const uint4 *gp = reinterpret_cast<const uint4 *>(gsrc) + 2u * static_cast<uint32_t>(idx);
+    float4 *xb = reinterpret_cast<float4 *>(X) + (idx & (Gm::G - 1)) * Gm::PITCH + (idx >> Gm::LOG_G);
+    for (uint32_t gc = idx; gc < n_full; gc += B * STRIDE, gp += 2u * B * STRIDE, xb += B * (STRIDE / Gm::G)) {
+        uint4 v[2 * B];
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            if (gc + j * STRIDE < n_full) {
+                v[2 * j] = __ldg(gp + 2u * j * STRIDE);
+                v[2 * j + 1] = __ldg(gp + 2u * j * STRIDE + 1);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < B; j++) {
+            if (gc + j * STRIDE < n_full) {
+                float4 *o = xb + j * (STRIDE / Gm::G);
+                o[0] = make_float4(__uint_as_float(v[2 * j].x), __uint_as_float(v[2 * j].y), __uint_as_float(v[2 * j].z), __uint_as_float(v[2 * j].w));
+                o[Gm::G * Gm::PITCH] = make_float4(__uint_as_float(v[2 * j + 1].x), __uint_as_float(v[2 * j + 1].y), __uint_as_float(v[2 * j + 1].z), __uint_as_float(v[2 * j + 1].w));
+            }
+        }
+    }
+    if (idx == 0) { // the last 0..3 samples, one at a time
+        for (uint32_t l = 4 * n_full; l < n_dec; l++) {
+            const uint32_t pr = (l >> 1) & (Gm::DR / 2 - 1);
+            float4 *el = reinterpret_cast<float4 *>(X) + ((pr & 1) * Gm::G + (pr >> 1)) * Gm::PITCH + (l >> Gm::LOG_DR);
+            reinterpret_cast<float2 *>(el)[l & 1] = __ldg(reinterpret_cast<const float2 *>(gsrc) + l);
+        }
+    }
+}
+
 template <int D, int R, int NT, int LMAX, bool MIX>
 __device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
                                                  uint64_t n_tile0, const LeanPhase *lp, const double2 *ttab,
@@ -755,6 +795,8 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
             if (!EXACT && lean && (lead & 3) == 0 && (!lean_mix || lphase->ok)) {
                 if (lean_mix) decode_tile_lean<D, R, NT, LMAX, true>(a, raw, lead, n_dec, g.n_tile0, lphase, ttab, X, tid);
                 else decode_tile_lean<D, R, NT, LMAX, false>(a, raw, lead, n_dec, g.n_tile0, lphase, ttab, X, tid);
+            } else if (!staged && a.n_shift == 0 && lead == 0) {
+                decode_cf32_copy<Gm, NT>(raw, n_dec, X, tid);
             } else if (EXACT && staged && (lead & 3) == 0) {
                 const uint32_t raw_addr = smem_u32(raw) + pb * lead;
                 float4 *X4 = reinterpret_cast<float4 *>(X);
