@@ -128,6 +128,23 @@ constexpr int pitch_for(int G, int cols)
     return p;
 }
 
+// Outputs per tile.  R*NT by default; when the filter length is known at compile time the tile is trimmed so that
+// its raw span, (T-1)*D + L samples, is a whole number of decode iterations (4*NT samples each): no nearly empty
+// last iteration for one warp to run while the others wait at the barrier.  Kept a multiple of R (a thread's
+// outputs never straddle a unit) and even (16-byte aligned output rows).
+constexpr int tile_outputs(int D, int R, int NT, int LS)
+{
+    const int t_out = R * NT;
+    if (LS <= 0) return t_out;
+    const int iters = ((t_out - 1) * D + LS) / (4 * NT);
+    if (iters < 1 || iters * 4 * NT < LS + D) return t_out;
+    int t = (iters * 4 * NT - LS) / D + 1;
+    if (t > t_out) t = t_out;
+    t -= t % R;
+    t -= t % 2;
+    return t >= t_out / 2 ? t : t_out;
+}
+
 template <int D, int R, int NT, int LMAX = kMaxTapPairs>
 struct FirGeom {
     static constexpr int DR = D * R; // polyphase period
@@ -135,6 +152,7 @@ struct FirGeom {
     static constexpr int LOG_DR = (DR == 16) ? 4 : (DR == 32) ? 5 : 6;
     static constexpr int LOG_G = LOG_DR - 2;
     static constexpr int T_OUT = R * NT;
+    static constexpr int T_TILE = tile_outputs(D, R, NT, LMAX == kMaxTapPairs ? 0 : LMAX); // outputs a tile really holds
     // samples the tile's threads touch: whole tap blocks of D for the longest filter this layout holds, plus
     // the tail of a partial last decode group where one can exist
     static constexpr int SPAN = (T_OUT - 1) * D + (LMAX + D - 1) / D * D + ((LMAX % 4 || D % 4) ? 3 : 0);
@@ -756,7 +774,7 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         double c, s;
         sincos_f64k(__dmul_rn(static_cast<double>(4 * tid), a.ratio[0]), a.sincos, a.k, c, s);
         ttab[tid] = make_double2(c, s);
-        if (tid == 0 && blockIdx.x < a.n_tiles) tile_phase(tile_geo<D, Gm::T_OUT>(a, blockIdx.x));
+        if (tid == 0 && blockIdx.x < a.n_tiles) tile_phase(tile_geo<D, Gm::T_TILE>(a, blockIdx.x));
     }
     __syncthreads();
 
@@ -777,10 +795,10 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
     };
 
     uint64_t it = 0;
-    if (tid == 0 && blockIdx.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, blockIdx.x));
+    if (tid == 0 && blockIdx.x < a.n_tiles) issue(tile_geo<D, Gm::T_TILE>(a, blockIdx.x));
 
     for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-        const TileGeo g = tile_geo<D, Gm::T_OUT>(a, tile);
+        const TileGeo g = tile_geo<D, Gm::T_TILE>(a, tile);
         const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + a.L;
         const uint32_t n_dec = static_cast<uint32_t>(min(span, a.src_end - g.n_tile0));
         const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * pb;
@@ -823,10 +841,10 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         }
         __syncthreads();
         // the raw bytes are consumed: fetch the next tile's while this one is filtered
-        if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x));
+        if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_TILE>(a, tile + gridDim.x));
         // the next tile's phase state: another warp's spare lane, so no warp carries both chores into the barrier
         if (lean_mix && tid == (NT > 32 ? 32 : 0) && tile + gridDim.x < a.n_tiles)
-            tile_phase(tile_geo<D, Gm::T_OUT>(a, tile + gridDim.x));
+            tile_phase(tile_geo<D, Gm::T_TILE>(a, tile + gridDim.x));
 
         // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
         fir_tile<D, R, NT, LMAX, EXACT, LS>(a, taps, g, X, tid, tid);
@@ -969,7 +987,7 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
         for (int b = 0; b < 64; b++)
             if ((uint64_t(1) << b) == n_call) a.ncall_log2 = b;
     a.total_out = total_out;
-    const uint64_t t_out = static_cast<uint64_t>(R) * lp.shape.NT;
+    const uint64_t t_out = static_cast<uint64_t>(tile_outputs(static_cast<int>(D), static_cast<int>(R), lp.shape.NT, a.L == 40 ? 40 : 0)); // as FirGeom::T_TILE of the kernel launch_fir_dr picks
     a.tiles_per_unit = static_cast<uint32_t>((n_call + t_out - 1) / t_out);
     a.n_tiles = a.contiguous ? (total_out + t_out - 1) / t_out : n_units * a.tiles_per_unit;
     const uint64_t pb = pair_bytes(fmt);
