@@ -624,10 +624,13 @@ __device__ __forceinline__ void general_block(const float2 *__restrict__ X, int 
     }
 }
 
-// LS > 0: the filter length is a compile-time constant and the whole tap schedule unrolls
-template <int D, int R, int NT, int LMAX, bool EXACT, int LS>
+// LS > 0: the filter length is a compile-time constant and the whole tap schedule unrolls.
+// TRUNC: the same schedule with every MAC predicated on its sample existing for this read (s < s_end): what a
+// warp runs when one of its threads owns the truncated tail of a unit, instead of sending that one thread
+// through the general loop while the other 31 wait.
+template <int D, int R, int NT, int LMAX, bool EXACT, int LS, bool TRUNC>
 __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid, const FirTaps &taps, float2 one,
-                                           float2 (&acc)[R])
+                                           float2 (&acc)[R], int s_end)
 {
     constexpr int Q = (LS + D - 1) / D, LREM = LS - (Q - 1) * D, NB = R - 1 + Q;
 #pragma unroll
@@ -640,7 +643,8 @@ __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid
             if (qb < 0 || qb >= Q) continue;
 #pragma unroll
             for (int p = 0; p < D; p++)
-                if (p < (qb == Q - 1 ? LREM : D)) acc[r] = mac<EXACT>(acc[r], v[p], taps.t[qb * D + p], one);
+                if (p < (qb == Q - 1 ? LREM : D) && (!TRUNC || b * D + p < s_end))
+                    acc[r] = mac<EXACT>(acc[r], v[p], taps.t[qb * D + p], one);
         }
     }
 }
@@ -714,10 +718,12 @@ __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, 
     #pragma unroll
         for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f); // Complex::zero(), filter.rs:112
 
-        if (LS > 0 && s_lim >= s_total) {
-            fir_static<D, R, NTG, LMAX, EXACT, (LS > 0 ? LS : 1)>(X, xidx, taps, one, acc);
-        } else { // also the tail of a read: outputs whose taps run past the end of the unit's raw buffer
-            const int s_end = static_cast<int>(min(static_cast<int64_t>(s_total), s_lim));
+        // the tail of a read: outputs whose taps run past the end of the unit's raw buffer stop there
+        const int s_end = static_cast<int>(min(static_cast<int64_t>(s_total), s_lim));
+        if (LS > 0) {
+            if (!__any_sync(__activemask(), s_lim < s_total)) fir_static<D, R, NTG, LMAX, EXACT, (LS > 0 ? LS : 1), false>(X, xidx, taps, one, acc, s_end);
+            else fir_static<D, R, NTG, LMAX, EXACT, (LS > 0 ? LS : 1), true>(X, xidx, taps, one, acc, s_end);
+        } else {
             fir_dynamic<D, R, NTG, LMAX, EXACT>(X, xidx, Q, Lrem, s_end, taps, one, acc);
         }
         float2 *o = a.out + g.out0 + static_cast<uint64_t>(R * tid);
