@@ -57,6 +57,13 @@ WORKLOADS = {
         stages=[("lowpass", 20_000_000, 8, 40), ("lowpass", 500_000, 32, 40)], sink=("sparkfft", 4, 2, (0.001, 0.01)),
         tones=[(0.1e6, 160, 1_000_000), (90e6, 3000, 0)], noise=40, seed=0x5EED0005,
         out_bytes_per_unit=4, cpu_units=4096, ref_units_per_thread=256),
+    # BASELINE.json configs[0] (the reference's own example chain) at capture scale: overlapping windows
+    "cfg1": dict(
+        title="synthetic cf32 21 MS/s: shift 280000 | lowpass -power 200 -decimate 32 200000 | sparkfft -width 64 -stride 16 -range 0.01:3",
+        fmt=CF32, rate=21_000_000, samples=2**27,
+        stages=[("shift", 280_000), ("lowpass", 200_000, 32, 400)], sink=("sparkfft", 64, 16, (0.01, 3.0)),
+        tones=[(-250e3, 6000, 2000), (-310e3, 6000, 2000), (3e6, 9000, 0)], noise=300, seed=0x5EED0001,
+        out_bytes_per_unit=64, cpu_units=2048, ref_units_per_thread=128),
     # BASELINE.json configs[2] shape
     "cfg3": dict(
         title="synthetic cu8 2.4 MS/s multi-tone: sparkfft -width 4096 -stride 1024 -range 2:500",

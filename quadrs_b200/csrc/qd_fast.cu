@@ -858,6 +858,49 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
     }
 }
 
+// ---------------------------------------------------------------------------- truncated window tails
+// One warp per window: output k = n - T + r of the read (off, n) is the one whose taps stop at the end of that
+// read's raw buffer, J = (T - r) * D + L/2 < L of them (filter.rs:68-71,107-124).  The T tails of a window
+// share their T*D + L/2 samples, so the warp decodes and mixes those once into shared memory, then lane r sums
+// tail r in ascending tap order.  Always the exact arithmetic: decode, fl64(n * ratio) and an f64 sin/cos per
+// sample and shift, product and sum rounded separately.
+struct TailArgs {
+    const uint8_t *src;
+    uint64_t src_base;
+    int fmt, n_shift;
+    double ratio[kMaxLeadShifts];
+    const double *sincos;
+    uint32_t L, D, T, span; // span = T*D + L/2 samples per window
+    uint64_t off0, S, n_call, n_units;
+    float2 *out; // [n_units][T]
+    float2 one;
+};
+constexpr int kTailWarps = 4;
+
+__global__ void __launch_bounds__(32 * kTailWarps) fk_tail(const __grid_constant__ TailArgs a, const __grid_constant__ FirTaps taps)
+{
+    extern __shared__ float2 tail_smem[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t u = static_cast<uint64_t>(blockIdx.x) * kTailWarps + w;
+    if (u >= a.n_units) return;
+    float2 *x = tail_smem + static_cast<size_t>(w) * a.span;
+    const uint32_t i0 = a.L - a.L / 2;
+    const uint64_t n0 = (a.off0 + u * a.S + a.n_call - a.T) * a.D + i0; // sample under tap 0 of the first tail
+    for (uint32_t l = lane; l < a.span; l += 32) {
+        float2 v = decode_sample(a.src, a.fmt, n0 + l - a.src_base);
+        for (int sft = 0; sft < a.n_shift; sft++) v = cmul_exact(v, phasor_exact(n0 + l, a.ratio[sft], a.sincos));
+        x[l] = v;
+    }
+    __syncwarp();
+    for (uint32_t r = lane; r < a.T; r += 32) {
+        const uint32_t J = min(a.L, (a.T - r) * a.D + a.L / 2);
+        const float2 *xr = x + r * a.D;
+        float2 acc = make_float2(0.0f, 0.0f);
+        for (uint32_t j = 0; j < J; j++) acc = fma2(mul2(xr[j], taps.t[j]), a.one, acc); // fl(acc + fl(x * f)), filter.rs:119
+        a.out[u * a.T + r] = acc;
+    }
+}
+
 // ---------------------------------------------------------------------------- host side
 
 // (decimate) -> outputs per thread R and threads per CTA; R * NT * D ~ 8192 raw samples per tile
@@ -914,6 +957,11 @@ struct FastPlan {
     // The top stage's outputs do not depend on the read they belong to (no truncated positions), so it is
     // materialised once as a contiguous stream and windows are taken from it at the sink's stride.
     bool stream_top = false;
+    // Overlapping windows behind ONE filter that does have truncated positions (T > 0): all but the last T
+    // samples of a window are still read-independent, so the stream is shared as above and the last T samples of
+    // every window -- the ones whose taps stop at the end of that window's own raw buffer -- are computed on
+    // their own (fk_tail) into a patch matrix the STFT kernel reads in their place.
+    bool stream_tail = false;
 };
 
 static bool lp_info(const Stage &st, LpInfo *o)
@@ -952,6 +1000,10 @@ static FastPlan fast_plan(const Chain &c, uint64_t unit_len, uint64_t stride, ui
         f.stream_top = true;
     } else {
         f.stream_top = top.T == 0 && stride != unit_len && n_units > 1;
+        if (!f.stream_top && c.allow_tail && top.T > 0 && top.T < unit_len && stride < unit_len && n_units > 1) {
+            f.stream_top = true;
+            f.stream_tail = true;
+        }
     }
     if (!f.stream_top && unit_len % static_cast<uint64_t>(top.shape.R) != 0) return f;
     // absolute sample 0 must sit on a 16-byte boundary so every tile's bytes can be bulk-copied
@@ -1188,10 +1240,40 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
             }
             d_top = d_out;
             pitch = stride;
+            if (f.stream_tail) {
+                QD_TRY(c.ensure(c.pipe_tail[j], nu * top.T * sizeof(float2)));
+                TailArgs ta;
+                memset(&ta, 0, sizeof ta);
+                ta.src = d_src;
+                ta.src_base = src_base;
+                ta.fmt = s.format;
+                ta.n_shift = f.n_shift;
+                for (int i = 0; i < f.n_shift; i++) ta.ratio[i] = ratios[i];
+                ta.sincos = c.ctx->d_sincos;
+                ta.L = top.L, ta.D = top.D, ta.T = top.T;
+                ta.span = top.T * top.D + top.L / 2;
+                ta.off0 = soff, ta.S = stride, ta.n_call = unit_len, ta.n_units = nu;
+                ta.out = static_cast<float2 *>(c.pipe_tail[j].p);
+                ta.one = make_float2(1.0f, 1.0f);
+                FirTaps tt;
+                memset(&tt, 0, sizeof tt);
+                for (uint32_t i = 0; i < top.L; i++) tt.t[i] = make_float2(top.st->taps[i], top.st->taps[i]);
+                const size_t tsm = static_cast<size_t>(kTailWarps) * ta.span * sizeof(float2);
+                if (tsm > 48 * 1024) QD_CUDA(cudaFuncSetAttribute(fk_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tsm)));
+                fk_tail<<<static_cast<unsigned>((nu + kTailWarps - 1) / kTailWarps), 32 * kTailWarps, tsm, c.stream>>>(ta, tt);
+                QD_LAUNCHED();
+                c.seg_tail = ta.out;
+                c.seg_tail_len = top.T;
+            }
         }
         QD_TRY(c.prof_end("fk_fir (fused decode+mix+FIR-decimate)"));
         QD_CUDA(cudaEventRecord(c.ev_compute[j], c.stream)); // the raw staging buffer may be refilled
-        if (on_segment) QD_TRY(on_segment(c, user, j, u0, nu, d_top, pitch));
+        if (on_segment) {
+            const int rc = on_segment(c, user, j, u0, nu, d_top, pitch);
+            c.seg_tail = nullptr;
+            c.seg_tail_len = 0;
+            if (rc != QD_OK) return rc;
+        }
     }
     *units_done = n_full;
     return QD_OK;

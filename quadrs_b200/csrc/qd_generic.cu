@@ -653,6 +653,8 @@ static int fast_segment_sink(Chain &c, void *user, int j, uint64_t u0, uint64_t 
     fill_fft_args(c, sink, W, &fa);
     fa.in = d_top;
     fa.in_pitch = pitch; // unit_len for a [units][W] matrix, the window stride for a contiguous stream
+    fa.tail = c.seg_tail; // truncated window tails patched over the stream (run_units_fast)
+    fa.tail_len = c.seg_tail_len;
     fa.raw = ctx->raw;
     fa.raw_fmt = ctx->raw_fmt;
     fa.raw_first = ctx->raw_first;
@@ -912,7 +914,10 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
         float2 *direct = (sink.kind == SINK_SAMPLES && sink.space == QD_SPACE_DEVICE)
                              ? reinterpret_cast<float2 *>(sink.samples_out)
                              : nullptr;
+        // the fast STFT kernel can take a window's truncated tail from a patch matrix (see run_units_fast)
+        c.allow_tail = fft_sink && sink.kind == SINK_SPARK && !sink.windowed && unit_len <= 4096 && is_pow2(unit_len);
         QD_TRY(run_units_fast(c, off0, stride, n_units, unit_len, direct, fast_segment_sink, &ctx, &done));
+        c.allow_tail = false;
         used_pipeline = done > 0;
         produced = sink.kind == SINK_SAMPLES ? done * unit_len : done;
         if (used_pipeline) {

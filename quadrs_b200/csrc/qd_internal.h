@@ -151,7 +151,13 @@ struct Chain {
     cudaEvent_t ev_entry = nullptr, ev_exit = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_sink[2] = {nullptr, nullptr},
                 ev_d2h[2] = {nullptr, nullptr};
-    Buf pipe_in[2], pipe_mid[2], pipe_out[2], pipe_idx[2], pipe_mag[2];
+    Buf pipe_in[2], pipe_mid[2], pipe_out[2], pipe_idx[2], pipe_mag[2], pipe_tail[2];
+    // overlapping windows behind a filter with truncated positions: the windows are cut from one stream and the
+    // last `seg_tail_len` samples of every window come from a patch matrix [units][seg_tail_len] (run_units_fast
+    // sets these for the sink of the current segment; allow_tail: the sink understands them)
+    const float2 *seg_tail = nullptr;
+    uint32_t seg_tail_len = 0;
+    bool allow_tail = false;
     void *h_pin2[2] = {nullptr, nullptr};
     size_t h_pin2_cap[2] = {0, 0};
     int ensure_pipeline();
@@ -215,6 +221,8 @@ enum { EPI_SPARK = 0, EPI_LEVELS = 1, EPI_TAKE = 2 };
 
 struct FftArgs {
     const float2 *in;     // cf32 windows: window u starts at in + u * in_pitch
+    const float2 *tail;   // nullable: the last tail_len samples of window u are tail[u * tail_len ..] instead
+    uint32_t tail_len;
     uint64_t in_pitch;
     const uint8_t *raw;   // or raw capture bytes (decoded on load): window u starts at sample raw_first + u * in_pitch
     int raw_fmt;

@@ -36,6 +36,7 @@ __device__ __forceinline__ uint32_t digitrev4(uint32_t x, int nd)
 __device__ __forceinline__ float2 load_elem(const FftArgs &a, uint64_t u, uint32_t n)
 {
     if (a.raw) return decode_sample(a.raw, a.raw_fmt, a.raw_first + u * a.in_pitch + n);
+    if (a.tail_len && n >= a.W - a.tail_len) return a.tail[u * a.tail_len + (n - (a.W - a.tail_len))];
     return a.in[u * a.in_pitch + n];
 }
 
@@ -46,7 +47,8 @@ __device__ __forceinline__ void load_group_m(const FftArgs &a, uint64_t u, uint3
 #pragma unroll
     for (int i = 0; i < N; i++) {
         const uint32_t n = first + step * i;
-        e[place(i)] = MODE < 0 ? a.in[u * a.in_pitch + n] : decode_sample(a.raw, MODE, a.raw_first + u * a.in_pitch + n);
+        if (MODE < 0) e[place(i)] = (a.tail_len && n >= a.W - a.tail_len) ? a.tail[u * a.tail_len + (n - (a.W - a.tail_len))] : a.in[u * a.in_pitch + n];
+        else e[place(i)] = decode_sample(a.raw, MODE, a.raw_first + u * a.in_pitch + n);
     }
 }
 template <int N, typename Place>
