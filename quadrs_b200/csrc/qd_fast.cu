@@ -859,7 +859,7 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
 }
 
 // ---------------------------------------------------------------------------- truncated window tails
-// One warp per window: output k = n - T + r of the read (off, n) is the one whose taps stop at the end of that
+// A few windows per warp: output k = n - T + r of the read (off, n) is the one whose taps stop at the end of that
 // read's raw buffer, J = (T - r) * D + L/2 < L of them (filter.rs:68-71,107-124).  The T tails of a window
 // share their T*D + L/2 samples, so the warp decodes and mixes those once into shared memory, then lane r sums
 // tail r in ascending tap order.  Always the exact arithmetic: decode, fl64(n * ratio) and an f64 sin/cos per
@@ -871,6 +871,8 @@ struct TailArgs {
     double ratio[kMaxLeadShifts];
     const double *sincos;
     uint32_t L, D, T, span; // span = T*D + L/2 samples per window
+    uint32_t log_d;         // D = 2^log_d
+    uint32_t wpw;           // windows per warp: min(32 / T, 8)
     uint64_t off0, S, n_call, n_units;
     float2 *out; // [n_units][T]
     float2 one;
@@ -881,23 +883,31 @@ __global__ void __launch_bounds__(32 * kTailWarps) fk_tail(const __grid_constant
 {
     extern __shared__ float2 tail_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t u = static_cast<uint64_t>(blockIdx.x) * kTailWarps + w;
-    if (u >= a.n_units) return;
-    float2 *x = tail_smem + static_cast<size_t>(w) * a.span;
+    // a warp takes wpw consecutive windows, so that wpw * T of its lanes run summation loops
+    const uint64_t u0 = (static_cast<uint64_t>(blockIdx.x) * kTailWarps + w) * a.wpw;
+    if (u0 >= a.n_units) return;
+    const uint32_t nw = static_cast<uint32_t>(min(static_cast<uint64_t>(a.wpw), a.n_units - u0));
+    // sample l of a window sits at l + l/D: the lanes of the summation loop read D samples apart, which without
+    // the skew is one shared-memory bank
+    const uint32_t pitch = a.span + (a.span >> a.log_d) + 1;
+    float2 *x = tail_smem + static_cast<size_t>(w) * a.wpw * pitch;
     const uint32_t i0 = a.L - a.L / 2;
-    const uint64_t n0 = (a.off0 + u * a.S + a.n_call - a.T) * a.D + i0; // sample under tap 0 of the first tail
-    for (uint32_t l = lane; l < a.span; l += 32) {
-        float2 v = decode_sample(a.src, a.fmt, n0 + l - a.src_base);
-        for (int sft = 0; sft < a.n_shift; sft++) v = cmul_exact(v, phasor_exact(n0 + l, a.ratio[sft], a.sincos));
-        x[l] = v;
+    for (uint32_t g = 0; g < nw; g++) {
+        const uint64_t n0 = (a.off0 + (u0 + g) * a.S + a.n_call - a.T) * a.D + i0; // sample under tap 0 of the first tail
+        for (uint32_t l = lane; l < a.span; l += 32) {
+            float2 v = decode_sample(a.src, a.fmt, n0 + l - a.src_base);
+            for (int sft = 0; sft < a.n_shift; sft++) v = cmul_exact(v, phasor_exact(n0 + l, a.ratio[sft], a.sincos));
+            x[g * pitch + l + (l >> a.log_d)] = v;
+        }
     }
     __syncwarp();
-    for (uint32_t r = lane; r < a.T; r += 32) {
+    const uint32_t g = static_cast<uint32_t>(lane) / a.T, r = static_cast<uint32_t>(lane) % a.T;
+    if (g < nw && a.T <= 32) {
         const uint32_t J = min(a.L, (a.T - r) * a.D + a.L / 2);
-        const float2 *xr = x + r * a.D;
+        const float2 *xg = x + g * pitch;
         float2 acc = make_float2(0.0f, 0.0f);
-        for (uint32_t j = 0; j < J; j++) acc = fma2(mul2(xr[j], taps.t[j]), a.one, acc); // fl(acc + fl(x * f)), filter.rs:119
-        a.out[u * a.T + r] = acc;
+        for (uint32_t j = 0, l = r * a.D; j < J; j++, l++) acc = fma2(mul2(xg[l + (l >> a.log_d)], taps.t[j]), a.one, acc); // fl(acc + fl(x * f)), filter.rs:119
+        a.out[(u0 + g) * a.T + r] = acc;
     }
 }
 
@@ -1000,7 +1010,7 @@ static FastPlan fast_plan(const Chain &c, uint64_t unit_len, uint64_t stride, ui
         f.stream_top = true;
     } else {
         f.stream_top = top.T == 0 && stride != unit_len && n_units > 1;
-        if (!f.stream_top && c.allow_tail && top.T > 0 && top.T < unit_len && stride < unit_len && n_units > 1) {
+        if (!f.stream_top && c.allow_tail && top.T > 0 && top.T <= 32 && top.T < unit_len && stride < unit_len && n_units > 1) {
             f.stream_top = true;
             f.stream_tail = true;
         }
@@ -1252,15 +1262,19 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
                 ta.sincos = c.ctx->d_sincos;
                 ta.L = top.L, ta.D = top.D, ta.T = top.T;
                 ta.span = top.T * top.D + top.L / 2;
+                ta.log_d = 0;
+                while ((1u << ta.log_d) < top.D) ta.log_d++;
                 ta.off0 = soff, ta.S = stride, ta.n_call = unit_len, ta.n_units = nu;
                 ta.out = static_cast<float2 *>(c.pipe_tail[j].p);
                 ta.one = make_float2(1.0f, 1.0f);
                 FirTaps tt;
                 memset(&tt, 0, sizeof tt);
                 for (uint32_t i = 0; i < top.L; i++) tt.t[i] = make_float2(top.st->taps[i], top.st->taps[i]);
-                const size_t tsm = static_cast<size_t>(kTailWarps) * ta.span * sizeof(float2);
+                ta.wpw = std::max<uint32_t>(1, std::min<uint32_t>(32 / top.T, 8));
+                const size_t tsm = static_cast<size_t>(kTailWarps) * ta.wpw * (ta.span + (ta.span >> ta.log_d) + 1) * sizeof(float2);
                 if (tsm > 48 * 1024) QD_CUDA(cudaFuncSetAttribute(fk_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tsm)));
-                fk_tail<<<static_cast<unsigned>((nu + kTailWarps - 1) / kTailWarps), 32 * kTailWarps, tsm, c.stream>>>(ta, tt);
+                const uint64_t per_cta = static_cast<uint64_t>(kTailWarps) * ta.wpw;
+                fk_tail<<<static_cast<unsigned>((nu + per_cta - 1) / per_cta), 32 * kTailWarps, tsm, c.stream>>>(ta, tt);
                 QD_LAUNCHED();
                 c.seg_tail = ta.out;
                 c.seg_tail_len = top.T;
