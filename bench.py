@@ -57,6 +57,13 @@ WORKLOADS = {
         stages=[("lowpass", 20_000_000, 8, 40), ("lowpass", 500_000, 32, 40)], sink=("sparkfft", 4, 2, (0.001, 0.01)),
         tones=[(0.1e6, 160, 1_000_000), (90e6, 3000, 0)], noise=40, seed=0x5EED0005,
         out_bytes_per_unit=4, cpu_units=4096, ref_units_per_thread=256),
+    # configs[1]'s input through the metric's literal chain: shift + lowpass + sparkfft with overlapping windows
+    "cfg2s": dict(
+        title="synthetic cs8 20 MS/s: shift 1500000 | lowpass -power 20 -decimate 8 1000000 | sparkfft -width 64 -stride 16 -range 0.01:3",
+        fmt=CS8, rate=20_000_000, samples=2**30,
+        stages=[("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)], sink=("sparkfft", 64, 16, (0.01, 3.0)),
+        tones=[(1.6e6, 45, 0), (-4.1e6, 30, 0), (0.3e6, 20, 3000)], noise=6, seed=0x5EED0002,
+        out_bytes_per_unit=64, cpu_units=8192, ref_units_per_thread=512),
     # BASELINE.json configs[0] (the reference's own example chain) at capture scale: overlapping windows
     "cfg1": dict(
         title="synthetic cf32 21 MS/s: shift 280000 | lowpass -power 200 -decimate 32 200000 | sparkfft -width 64 -stride 16 -range 0.01:3",
