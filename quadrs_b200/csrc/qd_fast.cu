@@ -892,11 +892,19 @@ __global__ void __launch_bounds__(32 * kTailWarps) fk_tail(const __grid_constant
     const uint32_t pitch = a.span + (a.span >> a.log_d) + 1;
     float2 *x = tail_smem + static_cast<size_t>(w) * a.wpw * pitch;
     const uint32_t i0 = a.L - a.L / 2;
-    for (uint32_t g = 0; g < nw; g++) {
-        const uint64_t n0 = (a.off0 + (u0 + g) * a.S + a.n_call - a.T) * a.D + i0; // sample under tap 0 of the first tail
-        for (uint32_t l = lane; l < a.span; l += 32) {
-            float2 v = decode_sample(a.src, a.fmt, n0 + l - a.src_base);
-            for (int sft = 0; sft < a.n_shift; sft++) v = cmul_exact(v, phasor_exact(n0 + l, a.ratio[sft], a.sincos));
+    // all nw * span samples of the warp's windows in one flat loop (a window's span is often shorter than a warp)
+    const uint64_t n00 = (a.off0 + u0 * a.S + a.n_call - a.T) * a.D + i0; // sample under tap 0 of window u0's first tail
+    const uint64_t wstep = a.S * a.D;                                      // raw samples from one window to the next
+    {
+        uint32_t g = 0, l = lane;
+        for (uint32_t idx = lane; idx < nw * a.span; idx += 32, l += 32) {
+            while (l >= a.span) {
+                l -= a.span;
+                g++;
+            }
+            const uint64_t n = n00 + g * wstep + l;
+            float2 v = decode_sample(a.src, a.fmt, n - a.src_base);
+            for (int sft = 0; sft < a.n_shift; sft++) v = cmul_exact(v, phasor_exact(n, a.ratio[sft], a.sincos));
             x[g * pitch + l + (l >> a.log_d)] = v;
         }
     }

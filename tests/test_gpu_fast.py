@@ -222,6 +222,43 @@ def test_full_size_config4_shape_sampled_rows(Q):
         assert np.array_equal(idx[r - first], widx), f"row {r}"
 
 
+TAIL_CASES = [
+    # fmt, stages, W, S: overlapping windows behind one filter with truncated positions (stream + tail patch)
+    (O.CS8, [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)], 64, 16),      # T = 2
+    (O.CF32, [("shift", 280_000), ("lowpass", 200_000, 32, 400)], 64, 16),       # config 1: T = 6
+    (O.CU8, [("lowpass", 3_000_000, 2, 132)], 128, 32),                           # T = 32, the most the patch takes
+    (O.CS16, [("lowpass", 3_000_000, 2, 140)], 128, 32),                          # T = 34: every window on its own
+    (O.CS8, [("shift", -2_000_000), ("shift", 700_000), ("lowpass", 500_000, 4, 64)], 16, 1),   # T = 7, stride 1
+    (O.CS16, [("shift", 7_000_000), ("lowpass", 2_000_000, 16, 800)], 256, 255),  # T = 24, one sample of overlap
+    (O.CF32, [("lowpass", 1_000_000, 8, 10)], 8, 3),                              # T = 0: plain stream
+]
+
+
+@pytest.mark.parametrize("fmt,stages,W,S", TAIL_CASES)
+def test_overlapping_windows_stream_plus_tail(Q, fmt, stages, W, S):
+    """Bucket indices and magnitudes of overlapping windows are bit-identical to the oracle's per-window reads,
+    from the first window to the ragged ones at the end of the capture."""
+    n = _mult(stages) * (W + 300 * S) + 5000
+    raw, _ = synth_raw(fmt, n, rate=100e6)
+    scale = 3e4 if fmt == O.CS16 else (100.0 if fmt == O.CU8 else 1.0)
+    rng = (0.02 * scale * np.sqrt(W), 3.0 * scale * np.sqrt(W))
+    o = oracle_chain(raw, fmt, 100_000_000, stages)
+    g = gpu_chain(raw, fmt, 100_000_000, stages)
+    with kept_only():
+        try:
+            widx, wmag = o.spark_fft(W, S, rng)
+        except O.OracleError as e:
+            with pytest.raises(Q.QdError) as ge:
+                g.spark_fft(W, S, rng)
+            assert ge.value.code == e.code
+            return
+    idx, mag = g.spark_fft(W, S, rng, want_mag=True)
+    idx2, _ = g.spark_fft(W, S, rng)
+    assert idx.shape == widx.shape and idx.shape[0] > 250
+    assert np.array_equal(idx, widx) and np.array_equal(idx2, widx)
+    assert_bit_equal(mag, wmag, "magnitudes")
+
+
 # ---------------------------------------------------------------- FAST arithmetic mode
 FAST_CASES = [
     (O.CS8, 20_000_000, [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)], 0),                      # config 2
