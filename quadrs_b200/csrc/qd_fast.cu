@@ -496,6 +496,7 @@ __device__ __forceinline__ void decode_lean_exact(const FirArgs &a, uint32_t raw
     const float2 one = a.one;
     const int n_shift = a.n_shift;
     double nd = __ull2double_rn(n0 + static_cast<uint64_t>(4 * idx)); // absolute index of the group's first sample
+#pragma unroll 2
     for (; rp < rp_end; rp += GB * STRIDE, xb += STRIDE / Gm::G) {
         float2 x[4];
         unpack_group<FMT>(rp, x, one);
