@@ -27,8 +27,10 @@ namespace qd {
 constexpr int kMaxTapPairs = 1024;
 constexpr int kMaxLeadShifts = 4;
 
-struct FirTaps {
+struct alignas(16) FirTaps {
     float2 t[kMaxTapPairs]; // (f[j], f[j]) pairs, zero padded to Q*D
+    float s[kMaxTapPairs];  // the same taps once each: the run-time-length loop fetches four per constant load and
+                            // lets the packed instructions broadcast them
 };
 
 struct FirArgs {
@@ -668,9 +670,20 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
             load_block<D, R, NT, LMAX>(X + 2 * (tid + (b + k) / R), (R - 1 + k) % R, v);
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                const float2 *tp = taps.t + (b + k - r) * D;
+                const float *ts = taps.s + (b + k - r) * D;
+                if (D % 4 == 0) {
 #pragma unroll
-                for (int p = 0; p < D; p++) acc[r] = mac<EXACT>(acc[r], v[p], tp[p], one);
+                    for (int p = 0; p < D; p += 4) {
+                        const float4 f = *reinterpret_cast<const float4 *>(ts + p);
+                        acc[r] = mac<EXACT>(acc[r], v[p], make_float2(f.x, f.x), one);
+                        acc[r] = mac<EXACT>(acc[r], v[p + 1], make_float2(f.y, f.y), one);
+                        acc[r] = mac<EXACT>(acc[r], v[p + 2], make_float2(f.z, f.z), one);
+                        acc[r] = mac<EXACT>(acc[r], v[p + 3], make_float2(f.w, f.w), one);
+                    }
+                } else {
+#pragma unroll
+                    for (int p = 0; p < D; p++) acc[r] = mac<EXACT>(acc[r], v[p], make_float2(ts[p], ts[p]), one);
+                }
             }
         }
     }
@@ -1092,7 +1105,10 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     const bool exact = c.precision == QD_PRECISION_EXACT;
     // FAST mode leaves cs8 samples as integers in the kernel and carries the 1/127 of lib.rs:251 in the taps
     const float scale = (!exact && fmt == QD_FMT_CS8) ? 1.0f / 127.0f : 1.0f;
-    for (uint32_t j = 0; j < a.L; j++) taps.t[j] = make_float2(st.taps[j] * scale, st.taps[j] * scale);
+    for (uint32_t j = 0; j < a.L; j++) {
+        taps.t[j] = make_float2(st.taps[j] * scale, st.taps[j] * scale);
+        taps.s[j] = st.taps[j] * scale;
+    }
     switch (D) {
     case 2: return launch_fir_dr<2, 8, 128>(c, a, taps, exact);
     case 4: return launch_fir_dr<4, 8, 128>(c, a, taps, exact);
