@@ -359,10 +359,26 @@ struct Graph {
     std::vector<qd_stage> stages;
     qd_chain *chain = nullptr;
     bool dirty = true;
+    std::vector<int> devices{0}; // --gpus N: the chain is sharded over devices 0..N-1 inside this one process
 
+    Graph() = default;
+    Graph(const Graph &) = delete;
+    Graph &operator=(const Graph &) = delete;
     ~Graph()
     {
         if (chain) qd_chain_destroy(chain);
+    }
+    // a new `from` / `gen` starts a new graph (lib.rs:89-101 ignore the previous value)
+    void reset()
+    {
+        if (chain) qd_chain_destroy(chain);
+        chain = nullptr;
+        has_source = false;
+        src = qd_source{};
+        path.clear();
+        cos.clear();
+        stages.clear();
+        dirty = true;
     }
     // stage constructors validate eagerly, as Shift::new / LowPass::new do
     void rebuild()
@@ -372,7 +388,7 @@ struct Graph {
         src.path = path.c_str();
         src.gen_cos = cos.data();
         src.gen_n_cos = cos.size();
-        const int rc = qd_chain_create(&src, stages.data(), stages.size(), 0, &chain);
+        const int rc = qd_chain_create_sharded(&src, stages.data(), stages.size(), devices.data(), devices.size(), &chain);
         if (rc != QD_OK) throw Err(qd_last_error());
         dirty = false;
     }
@@ -387,7 +403,7 @@ void exec(Graph &g, const Command &c)
 {
     switch (c.op) {
     case Op::From:
-        g = Graph();
+        g.reset();
         g.has_source = true;
         g.src.kind = QD_SRC_FILE;
         g.src.format = c.format;
@@ -396,7 +412,7 @@ void exec(Graph &g, const Command &c)
         g.rebuild();
         break;
     case Op::Gen:
-        g = Graph();
+        g.reset();
         g.has_source = true;
         g.src.kind = QD_SRC_GEN;
         g.src.sample_rate = c.sample_rate;
@@ -440,10 +456,25 @@ void exec(Graph &g, const Command &c)
             uint64_t got = 0;
             rc = qd_sparkfft(g.chain, c.width, c.stride, c.min.has_value(), c.min.value_or(0), c.max.value_or(0), r0,
                              std::min(batch, rows - r0), idx.data(), nullptr, QD_SPACE_HOST, &got);
-            for (uint64_t r = 0; r < got; r++) {
+            // fft.rs:59 panics while it formats the first row that holds an out-of-range bin: the rows before it
+            // are on stdout, that row and everything after it never appear
+            uint64_t lim = got;
+            if (rc == QD_E_GLYPH_RANGE)
+                for (uint64_t r = 0; r < got && lim == got; r++)
+                    for (uint64_t b = 0; b < c.width; b++)
+                        if (idx[r * c.width + b] == 9) {
+                            lim = r;
+                            break;
+                        }
+            for (uint64_t r = 0; r < lim; r++) {
                 const size_t n = qd_format_row(idx.data() + r * c.width, c.width, line.data(), line.size());
                 fwrite(line.data(), 1, n, stdout);
                 fputc('\n', stdout);
+            }
+            if (rc == QD_E_GLYPH_RANGE) {
+                fflush(stdout);
+                fprintf(stderr, "thread 'main' panicked at src/fft.rs:59: %s\n", qd_last_error());
+                exit(101);
             }
             if (rc != QD_OK) throw Err(qd_last_error());
             if (got == 0) break;
@@ -484,9 +515,22 @@ int main(int argc, char **argv)
 {
     std::vector<std::string> args(argv + 1, argv + argc);
     bool parse_only = false;
-    if (!args.empty() && args[0] == "--parse-only") {
-        parse_only = true;
-        args.erase(args.begin());
+    int n_gpus = 1;
+    // options of this front end only (the reference has none); they precede the commands
+    while (!args.empty() && args[0].rfind("--", 0) == 0) {
+        if (args[0] == "--parse-only") {
+            parse_only = true;
+            args.erase(args.begin());
+        } else if (args[0] == "--gpus" && args.size() >= 2) {
+            n_gpus = atoi(args[1].c_str());
+            args.erase(args.begin(), args.begin() + 2);
+            if (n_gpus < 1 || n_gpus > 64) {
+                fprintf(stderr, "Error: --gpus takes a device count between 1 and 64\n");
+                return 1;
+            }
+        } else {
+            break;
+        }
     }
     std::vector<Command> cmds;
     try {
@@ -507,6 +551,8 @@ int main(int argc, char **argv)
     }
     try {
         Graph g;
+        g.devices.clear();
+        for (int d = 0; d < n_gpus; d++) g.devices.push_back(d);
         for (auto &c : cmds) exec(g, c);
     } catch (const Err &e) {
         fflush(stdout);

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define QD_ABI_VERSION 1
+#define QD_ABI_VERSION 2
 
 typedef struct { float re, im; } qd_cf32; /* num_complex::Complex<f32>, interleaved */
 
@@ -119,6 +119,21 @@ const char *qd_status_name(int status);
 /* Builds the lazy graph: From/Gen then the stages in order (the fold of quadrs.rs:48-56).
  * Performs Shift::new / LowPass::new / Gen::new checks (shift.rs:20-24, gen.rs:18-20). */
 int qd_chain_create(const qd_source *src, const qd_stage *stages, size_t n_stages, int device, qd_chain **out);
+/* The same graph sharded by sample range over several GPUs of one box, driven by ONE host process -- the
+ * reference's caller is one process folding commands into one sink (quadrs.rs:48-56 -> fft.rs:27-66 /
+ * lib.rs:178-213).  Every sink call on the handle cuts its unit range (sparkfft rows, write chunks, bucket
+ * windows, take_fft rows) into n_dev contiguous parts; device i evaluates part i on its own host thread and
+ * stream set, staging only the raw samples its units touch (filter-tap / FFT-window halo included), and its
+ * results land at their place in the caller's ONE output buffer or file.  Phase, truncation and end-of-capture
+ * arithmetic use absolute sample indices, so there is no collective and the result equals the one-device
+ * chain's bit for bit (EXACT and FAST).  Sources: HOST_MEM, FILE, GEN (a DEVICE_MEM capture lives on one
+ * device: n_dev must be 1).  Outputs must be host buffers.  devices[] may name a device more than once.
+ * Worker threads bind themselves to the CPUs local to their GPU (sysfs local_cpulist of its PCI function)
+ * before they allocate pinned staging, so that staging lands on the GPU's NUMA node. */
+int qd_chain_create_sharded(const qd_source *src, const qd_stage *stages, size_t n_stages, const int *devices,
+                            size_t n_dev, qd_chain **out);
+/* number of devices a chain runs on (1 for qd_chain_create) */
+int qd_chain_n_devices(const qd_chain *c, size_t *n_dev);
 void qd_chain_destroy(qd_chain *c);
 /* Runs the chain's kernels and copies on the caller's cudaStream_t (NULL is the legacy default
  * stream).  A new chain owns a private non-blocking stream until this is called. */

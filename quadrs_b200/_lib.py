@@ -30,7 +30,7 @@ PAIR_BYTES = {FMT_CF32: 8, FMT_CS8: 2, FMT_CU8: 2, FMT_CS16: 4}
 # every symbol include/quadrs_gpu.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
     "qd_last_error", "qd_abi_version", "qd_device_count", "qd_kernel_launches", "qd_status_name",
-    "qd_chain_create", "qd_chain_destroy", "qd_chain_set_stream", "qd_chain_set_precision", "qd_chain_synchronize", "qd_chain_set_option",
+    "qd_chain_create", "qd_chain_create_sharded", "qd_chain_n_devices", "qd_chain_destroy", "qd_chain_set_stream", "qd_chain_set_precision", "qd_chain_synchronize", "qd_chain_set_option",
     "qd_chain_profile", "qd_chain_profile_read", "qd_chain_len", "qd_chain_sample_rate", "qd_chain_taps", "qd_chain_read_at", "qd_chain_read_exact_at",
     "qd_sparkfft_rows", "qd_sparkfft", "qd_format_row", "qd_freq_levels", "qd_take_fft", "qd_write_cf32",
     "qd_write_file", "qd_shard_plan", "qd_synth_fill",
@@ -99,6 +99,8 @@ def lib():
     L.qd_kernel_launches.restype = u64
     L.qd_device_count.argtypes = [C.POINTER(i32)]
     L.qd_chain_create.argtypes = [C.POINTER(Source), C.POINTER(Stage), sz, i32, C.POINTER(vp)]
+    L.qd_chain_create_sharded.argtypes = [C.POINTER(Source), C.POINTER(Stage), sz, C.POINTER(i32), sz, C.POINTER(vp)]
+    L.qd_chain_n_devices.argtypes = [vp, C.POINTER(sz)]
     L.qd_chain_destroy.argtypes = [vp]
     L.qd_chain_destroy.restype = None
     L.qd_chain_set_stream.argtypes = [vp, vp]

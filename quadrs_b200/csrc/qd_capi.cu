@@ -17,8 +17,6 @@
 
 #include "qd_internal.h"
 
-struct qd_chain : qd::Chain {};
-
 namespace qd {
 
 static thread_local char tl_error[512] = "";
@@ -61,6 +59,7 @@ int device_ctx(int device, DeviceCtx **out)
     auto ctx = std::make_unique<DeviceCtx>();
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->local_cpus = device_local_cpus(device);
     double tab[4 * 256];
     sincos_table(tab);
     QD_CUDA(cudaMalloc(&ctx->d_sincos, sizeof tab));
@@ -191,6 +190,14 @@ static int first_bad_unit(const Chain &c, uint64_t off0, uint64_t stride, uint64
 
 using namespace qd;
 
+// applies one call to every shard of a sharded handle (settings, synchronisation)
+template <class F>
+static int each_shard(qd_chain *c, F fn)
+{
+    for (qd_chain *s : c->shards) QD_TRY(fn(s));
+    return QD_OK;
+}
+
 extern "C" {
 
 const char *qd_last_error(void) { return last_error(); }
@@ -238,11 +245,44 @@ int qd_chain_create(const qd_source *src, const qd_stage *stages, size_t n_stage
     return QD_OK;
 }
 
+int qd_chain_create_sharded(const qd_source *src, const qd_stage *stages, size_t n_stages, const int *devices,
+                            size_t n_dev, qd_chain **out)
+{
+    if (!out) return set_error(QD_E_INVALID_ARG, "out is null");
+    *out = nullptr;
+    if (!devices || n_dev == 0) return set_error(QD_E_INVALID_ARG, "no devices given");
+    if (n_dev > 64) return set_error(QD_E_INVALID_ARG, "at most 64 devices");
+    if (n_dev == 1) return qd_chain_create(src, stages, n_stages, devices[0], out);
+    if (!src) return set_error(QD_E_INVALID_ARG, "source is null");
+    if (src->kind == QD_SRC_DEVICE_MEM)
+        return set_error(QD_E_INVALID_ARG, "a DEVICE_MEM capture lives on one device: shard a HOST_MEM, FILE or GEN source, "
+                                           "or create one chain per device over its own resident range");
+    std::unique_ptr<qd_chain> c(new qd_chain());
+    c->device = devices[0];
+    for (size_t i = 0; i < n_dev; i++) {
+        qd_chain *child = nullptr;
+        const int rc = qd_chain_create(src, stages, n_stages, devices[i], &child);
+        if (rc != QD_OK) return rc; // ~Chain of the handle destroys the children made so far
+        c->shards.push_back(child);
+    }
+    *out = c.release();
+    return QD_OK;
+}
+
+int qd_chain_n_devices(const qd_chain *c, size_t *n_dev)
+{
+    if (!c || !n_dev) return set_error(QD_E_INVALID_ARG, "null argument");
+    *n_dev = c->sharded() ? c->shards.size() : 1;
+    return QD_OK;
+}
+
 void qd_chain_destroy(qd_chain *c) { delete c; }
+
 
 int qd_chain_set_stream(qd_chain *c, void *cuda_stream)
 {
     if (!c) return set_error(QD_E_INVALID_ARG, "chain is null");
+    if (c->sharded()) return set_error(QD_E_INVALID_ARG, "a sharded chain runs on its own per-device streams");
     std::lock_guard<std::mutex> lk(c->mu);
     QD_CUDA(cudaSetDevice(c->device));
     QD_CUDA(cudaStreamSynchronize(c->stream));
@@ -257,6 +297,7 @@ int qd_chain_set_precision(qd_chain *c, int precision)
     if (!c) return set_error(QD_E_INVALID_ARG, "chain is null");
     if (precision != QD_PRECISION_EXACT && precision != QD_PRECISION_FAST)
         return set_error(QD_E_INVALID_ARG, "unknown precision %d", precision);
+    if (c->sharded()) return each_shard(c, [&](qd_chain *s) { return qd_chain_set_precision(s, precision); });
     if (precision == QD_PRECISION_FAST && c->src.kind != QD_SRC_GEN &&
         (c->src.format == QD_FMT_CU8 || c->src.format == QD_FMT_CS16))
         return set_error(QD_E_INVALID_ARG,
@@ -270,6 +311,7 @@ int qd_chain_set_precision(qd_chain *c, int precision)
 int qd_chain_set_option(qd_chain *c, const char *key, int64_t value)
 {
     if (!c || !key) return set_error(QD_E_INVALID_ARG, "null argument");
+    if (c->sharded()) return each_shard(c, [&](qd_chain *s) { return qd_chain_set_option(s, key, value); });
     std::lock_guard<std::mutex> lk(c->mu);
     if (!strcmp(key, "use_fast")) c->use_fast = value != 0;
     else if (!strcmp(key, "segment_bytes") && value > 0) c->segment_bytes = static_cast<size_t>(value);
@@ -281,6 +323,7 @@ int qd_chain_set_option(qd_chain *c, const char *key, int64_t value)
 int qd_chain_synchronize(qd_chain *c)
 {
     if (!c) return set_error(QD_E_INVALID_ARG, "chain is null");
+    if (c->sharded()) return each_shard(c, [](qd_chain *s) { return qd_chain_synchronize(s); });
     QD_CUDA(cudaSetDevice(c->device));
     QD_CUDA(cudaStreamSynchronize(c->stream));
     return QD_OK;
@@ -289,6 +332,7 @@ int qd_chain_synchronize(qd_chain *c)
 int qd_chain_profile(qd_chain *c, int enable)
 {
     if (!c) return set_error(QD_E_INVALID_ARG, "chain is null");
+    if (c->sharded()) return each_shard(c, [&](qd_chain *s) { return qd_chain_profile(s, enable); });
     std::lock_guard<std::mutex> lk(c->mu);
     QD_CUDA(cudaSetDevice(c->device));
     QD_CUDA(cudaStreamSynchronize(c->stream));
@@ -300,6 +344,24 @@ int qd_chain_profile(qd_chain *c, int enable)
 int qd_chain_profile_read(qd_chain *c, uint64_t *regions, double *total_ms, char *kernel_name, size_t cap)
 {
     if (!c) return set_error(QD_E_INVALID_ARG, "chain is null");
+    if (c->sharded()) { // the devices run side by side: report the slowest one
+        uint64_t n_max = 0;
+        double ms_max = -1.0;
+        for (qd_chain *s : c->shards) {
+            uint64_t n = 0;
+            double ms = 0.0;
+            char name[256] = "";
+            QD_TRY(qd_chain_profile_read(s, &n, &ms, name, sizeof name));
+            if (ms > ms_max) {
+                ms_max = ms;
+                n_max = n;
+                if (kernel_name && cap) snprintf(kernel_name, cap, "%s", name);
+            }
+        }
+        if (regions) *regions = n_max;
+        if (total_ms) *total_ms = ms_max < 0 ? 0.0 : ms_max;
+        return QD_OK;
+    }
     std::lock_guard<std::mutex> lk(c->mu);
     QD_CUDA(cudaSetDevice(c->device));
     QD_CUDA(cudaStreamSynchronize(c->stream));
@@ -330,18 +392,21 @@ int qd_chain_profile_read(qd_chain *c, uint64_t *regions, double *total_ms, char
 int qd_chain_len(const qd_chain *c, uint64_t *len)
 {
     if (!c || !len) return set_error(QD_E_INVALID_ARG, "null argument");
+    if (c->sharded()) return chain_len(*c->shards[0], len);
     return chain_len(*c, len);
 }
 
 int qd_chain_sample_rate(const qd_chain *c, uint64_t *rate)
 {
     if (!c || !rate) return set_error(QD_E_INVALID_ARG, "null argument");
+    if (c->sharded()) c = c->shards[0];
     *rate = chain_rate(*c);
     return QD_OK;
 }
 
 int qd_chain_taps(const qd_chain *c, size_t stage, float *out, size_t cap, size_t *n)
 {
+    if (c && c->sharded()) c = c->shards[0];
     if (!c || stage >= c->stages.size() || c->stages[stage].kind != QD_STAGE_LOWPASS)
         return set_error(QD_E_INVALID_ARG, "stage %zu is not a lowpass", stage);
     const auto &t = c->stages[stage].taps;
@@ -355,6 +420,7 @@ int qd_chain_read_at(qd_chain *c, uint64_t off, qd_cf32 *buf, size_t n, int spac
     if (!c || (!buf && n) || !got) return set_error(QD_E_INVALID_ARG, "null argument");
     *got = 0;
     if (n == 0) return QD_OK;
+    if (c->sharded()) return qd_chain_read_at(c->shards[0], off, buf, n, space, got); // one unit: one device
     std::lock_guard<std::mutex> lk(c->mu);
     uint64_t v = 0;
     QD_TRY(chain_valid(*c, off, n, &v));
@@ -382,6 +448,7 @@ int qd_sparkfft_rows(const qd_chain *c, size_t width, uint64_t stride, uint64_t 
 {
     if (!c || !rows) return set_error(QD_E_INVALID_ARG, "null argument");
     if (stride == 0) return set_error(QD_E_ZERO_STRIDE, "stride 0 never terminates (fft.rs:65)");
+    if (c->sharded()) c = c->shards[0];
     uint64_t len = 0;
     QD_TRY(chain_len(*c, &len));
     // while i < len - width { ...; i += stride }  (fft.rs:27-28,65)
@@ -397,6 +464,32 @@ int qd_sparkfft(qd_chain *c, size_t width, uint64_t stride, int has_range, float
     if (!is_pow2(width)) // Radix4::new, fft.rs:25
         return set_error(QD_E_FFT_WIDTH, "Radix4 algorithm requires a power-of-two input size. Got %zu", width);
     if (stride == 0) return set_error(QD_E_ZERO_STRIDE, "stride 0 never terminates (fft.rs:65)");
+    if (c->sharded()) {
+        // rows [first_row, first_row + n) in contiguous parts, one per device, each into its place of idx_out
+        if (space != QD_SPACE_HOST) return set_error(QD_E_INVALID_ARG, "a sharded chain delivers into host buffers");
+        uint64_t len = 0;
+        QD_TRY(chain_len(*c->shards[0], &len));
+        const uint64_t total = len >= width ? (len > width ? (len - width + stride - 1) / stride : 0) : 1;
+        if (first_row >= total || n_rows == 0) return QD_OK;
+        const uint64_t n = std::min(n_rows, total - first_row);
+        if (!idx_out) return set_error(QD_E_INVALID_ARG, "idx_out is null");
+        const size_t parts = c->shards.size();
+        std::vector<uint64_t> got(parts, 0);
+        std::vector<int> rc;
+        std::vector<std::string> msg;
+        run_on_shards(*c, [&](size_t i, qd_chain *s) {
+            uint64_t a, b;
+            shard_range(n, parts, i, &a, &b);
+            if (b == a) return static_cast<int>(QD_OK);
+            return qd_sparkfft(s, width, stride, has_range, min, max, first_row + a, b - a, idx_out + a * width,
+                               mag_out ? mag_out + a * width : nullptr, space, &got[i]);
+        }, rc, msg);
+        // the reference stops at its first failing row: rows of later parts are not delivered
+        size_t bad = parts;
+        const int status = first_shard_error(rc, msg, &bad);
+        for (size_t i = 0; i < parts && i <= bad; i++) *rows_out += got[i];
+        return status;
+    }
     std::lock_guard<std::mutex> lk(c->mu);
     uint64_t len = 0;
     QD_TRY(chain_len(*c, &len));
@@ -457,6 +550,25 @@ int qd_freq_levels(qd_chain *c, size_t width, uint64_t stride, size_t levels, ui
     if (!is_pow2(width))
         return set_error(QD_E_FFT_WIDTH, "Radix4 algorithm requires a power-of-two input size. Got %zu", width);
     if (stride == 0) return set_error(QD_E_ZERO_STRIDE, "attempt to divide by zero (fft.rs:86)");
+    if (c->sharded()) {
+        if (space != QD_SPACE_HOST) return set_error(QD_E_INVALID_ARG, "a sharded chain delivers into host buffers");
+        uint64_t total = 0;
+        QD_TRY(qd_freq_levels(c->shards[0], width, stride, levels, 0, 0, nullptr, space, &total));
+        *total_out = total;
+        if (first >= total || n == 0) return QD_OK;
+        const uint64_t cnt = std::min(n, total - first);
+        if (!vals) return set_error(QD_E_INVALID_ARG, "vals is null");
+        const size_t parts = c->shards.size();
+        std::vector<int> rc;
+        std::vector<std::string> msg;
+        run_on_shards(*c, [&](size_t i, qd_chain *s) {
+            uint64_t a, b, t = 0;
+            shard_range(cnt, parts, i, &a, &b);
+            if (b == a) return static_cast<int>(QD_OK);
+            return qd_freq_levels(s, width, stride, levels, first + a, b - a, vals + a, space, &t);
+        }, rc, msg);
+        return first_shard_error(rc, msg, nullptr);
+    }
     std::lock_guard<std::mutex> lk(c->mu);
     uint64_t len = 0;
     QD_TRY(chain_len(*c, &len));
@@ -478,12 +590,11 @@ int qd_freq_levels(qd_chain *c, size_t width, uint64_t stride, size_t levels, ui
     return run_units(*c, first * stride, stride, nullptr, cnt, width, sink, &produced);
 }
 
-int qd_take_fft(qd_chain *c, int has_slice, uint64_t start, uint64_t end, size_t width, int windowing,
-                size_t output_len, float *out, int space)
+// rows [row0, row0 + n_rows) of take_fft; every row of the call is validated first, as the reference's `?` at
+// ffts.rs:62 fails the whole call.  out receives the rows of the range only.
+static int take_fft_rows(qd_chain *c, int has_slice, uint64_t start, uint64_t end, size_t width, int windowing,
+                         size_t output_len, size_t row0, size_t n_rows, float *out, int space)
 {
-    if (!c) return set_error(QD_E_INVALID_ARG, "chain is null");
-    // FftPlanner accepts any length (ffts.rs:25): powers of two run the radix-4 FFT, others a direct DFT
-    if (width == 0 || width > 16384) return set_error(QD_E_FFT_WIDTH, "take_fft width %zu unsupported (1..16384)", width);
     std::lock_guard<std::mutex> lk(c->mu);
     uint64_t len = 0;
     QD_TRY(chain_len(*c, &len));
@@ -511,6 +622,7 @@ int qd_take_fft(qd_chain *c, int has_slice, uint64_t start, uint64_t end, size_t
             return set_error(QD_E_SHORT_READ, "TODO: read-exact messed up: %zu (wanted) != %llu (read) at %llu", width,
                              (unsigned long long)v, (unsigned long long)offs[i]);
     }
+    if (n_rows == 0) return QD_OK;
     SinkArgs sink;
     sink.kind = SINK_TAKE;
     sink.width = width;
@@ -518,19 +630,79 @@ int qd_take_fft(qd_chain *c, int has_slice, uint64_t start, uint64_t end, size_t
     sink.space = space;
     sink.mag_out = out;
     uint64_t produced = 0;
-    return run_units(*c, 0, 0, offs.data(), output_len, width, sink, &produced);
+    return run_units(*c, 0, 0, offs.data() + row0, n_rows, width, sink, &produced);
 }
 
-int qd_write_cf32(qd_chain *c, size_t chunk, uint64_t first_chunk, uint64_t n_chunks, qd_cf32 *out, uint64_t cap,
-                  int space, uint64_t *n_out)
+int qd_take_fft(qd_chain *c, int has_slice, uint64_t start, uint64_t end, size_t width, int windowing,
+                size_t output_len, float *out, int space)
 {
-    if (!c || !n_out) return set_error(QD_E_INVALID_ARG, "null argument");
+    if (!c) return set_error(QD_E_INVALID_ARG, "chain is null");
+    // FftPlanner accepts any length (ffts.rs:25): powers of two run the radix-4 FFT, others a direct DFT
+    if (width == 0 || width > 16384) return set_error(QD_E_FFT_WIDTH, "take_fft width %zu unsupported (1..16384)", width);
+    if (!c->sharded()) return take_fft_rows(c, has_slice, start, end, width, windowing, output_len, 0, output_len, out, space);
+    if (space != QD_SPACE_HOST) return set_error(QD_E_INVALID_ARG, "a sharded chain delivers into host buffers");
+    const size_t parts = c->shards.size();
+    std::vector<int> rc;
+    std::vector<std::string> msg;
+    run_on_shards(*c, [&](size_t i, qd_chain *s) {
+        uint64_t a, b;
+        shard_range(output_len, parts, i, &a, &b);
+        return take_fft_rows(s, has_slice, start, end, width, windowing, output_len, a, b - a, out ? out + a * width : nullptr, space);
+    }, rc, msg);
+    return first_shard_error(rc, msg, nullptr);
+}
+
+// do_write's pull loop from sample offset `off`: at most n_reads reads of `chunk` samples, each starting where
+// the previous one ended (lib.rs:200-204).  The chain's mutex is held by the caller.
+static int write_from(qd_chain *c, size_t chunk, uint64_t off, uint64_t n_reads, qd_cf32 *out, uint64_t cap, int space,
+                      uint64_t *n_out)
+{
     *n_out = 0;
-    if (chunk == 0) return set_error(QD_E_INVALID_ARG, "chunk is 0");
-    std::lock_guard<std::mutex> lk(c->mu);
+    if (c->sharded()) {
+        // the run of FULL chunks goes to the devices in contiguous parts, each landing at its place of out[];
+        // whatever follows (the ragged last read and the read that trips lib.rs:203) is one device's work
+        if (space != QD_SPACE_HOST) return set_error(QD_E_INVALID_ARG, "a sharded chain delivers into host buffers");
+        qd_chain *c0 = c->shards[0];
+        uint64_t len = 0;
+        QD_TRY(chain_len(*c0, &len));
+        uint64_t good = 0;
+        if (off < len && n_reads) {
+            const uint64_t max_units = std::min<uint64_t>(n_reads, (len - off + chunk - 1) / chunk);
+            int bad = QD_OK;
+            QD_TRY(first_bad_unit(*c0, off, chunk, max_units, chunk, &good, &bad));
+            good = std::min<uint64_t>(good, cap / chunk);
+        }
+        if (good) {
+            if (!out) return set_error(QD_E_INVALID_ARG, "out is null");
+            const size_t parts = c->shards.size();
+            std::vector<uint64_t> got(parts, 0);
+            std::vector<int> rc;
+            std::vector<std::string> msg;
+            run_on_shards(*c, [&](size_t i, qd_chain *s) {
+                uint64_t a, b;
+                shard_range(good, parts, i, &a, &b);
+                if (b == a) return static_cast<int>(QD_OK);
+                std::lock_guard<std::mutex> lk(s->mu);
+                return write_from(s, chunk, off + a * chunk, b - a, out + a * chunk, (b - a) * chunk, space, &got[i]);
+            }, rc, msg);
+            QD_TRY(first_shard_error(rc, msg, nullptr));
+            for (size_t i = 0; i < parts; i++) *n_out += got[i];
+            if (*n_out != good * chunk) return set_error(QD_E_CUDA, "internal: sharded write produced %llu of %llu samples",
+                                                         (unsigned long long)*n_out, (unsigned long long)(good * chunk));
+        }
+        if (good < n_reads && off + good * chunk < len) {
+            uint64_t tail = 0;
+            std::lock_guard<std::mutex> lk(c0->mu);
+            const int rc = write_from(c0, chunk, off + good * chunk, n_reads - good, out ? out + good * chunk : nullptr,
+                                      cap - good * chunk, space, &tail);
+            *n_out += tail;
+            return rc;
+        }
+        return QD_OK;
+    }
     uint64_t len = 0;
     QD_TRY(chain_len(*c, &len));
-    uint64_t off = first_chunk * chunk, done = 0, left = n_chunks;
+    uint64_t done = 0, left = n_reads;
     // 1. the run of full chunks, as one batched launch sequence
     if (off < len && left) {
         uint64_t max_units = std::min<uint64_t>(left, (len - off + chunk - 1) / chunk);
@@ -574,37 +746,59 @@ int qd_write_cf32(qd_chain *c, size_t chunk, uint64_t first_chunk, uint64_t n_ch
     return QD_OK;
 }
 
+int qd_write_cf32(qd_chain *c, size_t chunk, uint64_t first_chunk, uint64_t n_chunks, qd_cf32 *out, uint64_t cap,
+                  int space, uint64_t *n_out)
+{
+    if (!c || !n_out) return set_error(QD_E_INVALID_ARG, "null argument");
+    *n_out = 0;
+    if (chunk == 0) return set_error(QD_E_INVALID_ARG, "chunk is 0");
+    std::lock_guard<std::mutex> lk(c->mu);
+    return write_from(c, chunk, first_chunk * chunk, n_chunks, out, cap, space, n_out);
+}
+
 int qd_write_file(qd_chain *c, const char *prefix, int overwrite, char *name_out, size_t name_cap)
 {
     if (!c || !prefix) return set_error(QD_E_INVALID_ARG, "null argument");
     if (strcmp(prefix, "-") == 0) return set_error(QD_E_UNIMPLEMENTED, "not implemented"); // lib.rs:179-181
     char name[4096];
-    snprintf(name, sizeof name, "%s.sr%llu.cf32", prefix, (unsigned long long)chain_rate(*c)); // lib.rs:194
+    snprintf(name, sizeof name, "%s.sr%llu.cf32", prefix, (unsigned long long)chain_rate(c->sharded() ? *c->shards[0] : *c)); // lib.rs:194
     if (name_out && name_cap) snprintf(name_out, name_cap, "%s", name);
     const int fd = open(name, O_WRONLY | O_CREAT | (overwrite ? 0 : O_EXCL), 0666); // lib.rs:186-192
     if (fd < 0) return set_error(errno == EEXIST ? QD_E_EXISTS : QD_E_IO, "%s: %s", name, strerror(errno));
     FILE *f = fdopen(fd, "wb");
+    if (!f) {
+        const int e = errno;
+        close(fd);
+        return set_error(QD_E_IO, "%s: %s", name, strerror(e));
+    }
     const size_t chunk = 0x1000; // lib.rs:201
-    const uint64_t batch = 512;  // chunks per device round trip
+    const uint64_t batch = 512 * (c->sharded() ? c->shards.size() : 1); // reads per device round trip
     std::vector<qd_cf32> host(chunk * batch);
     int rc = QD_OK;
-    for (uint64_t first = 0;; first += batch) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    uint64_t len = 0;
+    rc = chain_len(c->sharded() ? *c->shards[0] : *c, &len);
+    // `while off < len` (lib.rs:200): every batch continues at the sample where the previous one ended, so a
+    // ragged short read that happens to be the last read of a batch is still followed by the read that returns
+    // 0 samples and trips the reference's assert_ne! (lib.rs:203 -> QD_E_WRITE_SHORT)
+    for (uint64_t off = 0; rc == QD_OK && off < len;) {
         uint64_t n = 0;
-        rc = qd_write_cf32(c, chunk, first, batch, host.data(), host.size(), QD_SPACE_HOST, &n);
+        rc = write_from(c, chunk, off, batch, host.data(), host.size(), QD_SPACE_HOST, &n);
         if (n && fwrite(host.data(), sizeof(qd_cf32), n, f) != n) { // LE f32 re, im (lib.rs:206-209)
             rc = set_error(QD_E_IO, "%s: %s", name, strerror(errno));
             break;
         }
-        if (rc != QD_OK || n < chunk * batch) break;
+        off += n;
+        if (rc == QD_OK && n == 0) break; // cannot happen: a read of 0 samples is QD_E_WRITE_SHORT
     }
-    fclose(f);
+    if (fclose(f) != 0 && rc == QD_OK) rc = set_error(QD_E_IO, "%s: %s", name, strerror(errno));
     return rc;
 }
 
 int qd_shard_plan(const qd_source *src, const qd_stage *stages, size_t n_stages, int sink_kind, uint64_t unit_len,
                   uint64_t stride, uint32_t n_shards, uint32_t shard, qd_shard *out)
 {
-    if (!out || n_shards == 0 || shard >= n_shards || unit_len == 0)
+    if (!src || !out || n_shards == 0 || shard >= n_shards || unit_len == 0)
         return set_error(QD_E_INVALID_ARG, "qd_shard_plan: bad arguments");
     Chain c;
     qd_source s = *src;

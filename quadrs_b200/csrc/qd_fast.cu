@@ -50,6 +50,10 @@ struct FirArgs {
     int contiguous; // S == n_call: the units tile the output stream
     uint32_t tiles_per_unit;
     uint64_t n_tiles;
+    uint64_t tile_first; // contiguous mode: tiles are numbered from ABSOLUTE top-level output 0 (tile A holds outputs
+                         // [A*T, (A+1)*T)); the launch covers tiles tile_first .. tile_first + n_tiles - 1, the first and
+                         // last of them partly.  A tile's phase anchor, lane phasors and recurrences therefore depend
+                         // only on absolute position, never on where a launch (host segment, shard) starts.
     uint64_t total_out; // contiguous mode: outputs to compute (<= n_units * n_call)
     uint32_t raw_cap; // bytes per raw staging buffer
     float2 *out;      // [n_units][n_call]
@@ -165,12 +169,13 @@ struct FirGeom {
 };
 
 struct TileGeo {
-    uint64_t n_tile0; // absolute raw index of local sample 0 (first tap of the tile's first output)
-    uint64_t out0;    // index into out[]
-    uint64_t f0;      // flat output index of the tile's first output (contiguous mode)
+    uint64_t n_tile0; // absolute raw index of local sample 0 (first tap of the tile's first output slot)
+    int64_t f0;       // flat output index of the tile's first slot relative to the launch's first output: negative
+                      // for the launch's first tile when the launch starts inside it (contiguous mode)
     uint64_t unit;    // non-contiguous mode
     uint64_t u0;      // contiguous mode: unit that holds the tile's first output
-    uint32_t cnt;     // outputs in this tile
+    uint32_t cnt;     // output slots of this tile up to its last wanted output
+    uint32_t skip;    // leading slots that belong to an earlier launch (only the first tile of a launch)
 };
 
 template <int D, int T_OUT>
@@ -179,13 +184,14 @@ __device__ __forceinline__ TileGeo tile_geo(const FirArgs &a, uint64_t tile)
     TileGeo g;
     const uint32_t i0 = a.L - a.L / 2; // convoluted[L + k*D] is loop index L + k*D - L/2 (filter.rs:78-80,111)
     if (a.contiguous) {
-        g.f0 = tile * T_OUT;
-        const uint64_t total = a.total_out;
-        g.cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(T_OUT), total - g.f0));
-        g.out0 = g.f0;
+        const uint64_t first = (a.tile_first + tile) * T_OUT; // absolute top-level index of the tile's first slot
+        g.skip = first < a.off0 ? static_cast<uint32_t>(a.off0 - first) : 0u;
+        g.f0 = static_cast<int64_t>(first - a.off0);
+        g.cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(T_OUT), a.off0 + a.total_out - first));
         g.unit = 0;
-        g.u0 = a.ncall_log2 >= 0 ? (g.f0 >> a.ncall_log2) : g.f0 / a.n_call;
-        g.n_tile0 = (a.off0 + g.f0) * D + i0;
+        const uint64_t fpos = g.skip ? 0 : static_cast<uint64_t>(g.f0);
+        g.u0 = a.ncall_log2 >= 0 ? (fpos >> a.ncall_log2) : fpos / a.n_call;
+        g.n_tile0 = first * D + i0;
     } else {
         if (a.n_tiles <= 0xffffffffull) { // 32-bit division
             const uint32_t u = static_cast<uint32_t>(tile) / a.tiles_per_unit;
@@ -195,8 +201,8 @@ __device__ __forceinline__ TileGeo tile_geo(const FirArgs &a, uint64_t tile)
         }
         const uint32_t k0 = static_cast<uint32_t>(tile - g.unit * a.tiles_per_unit) * T_OUT;
         g.cnt = static_cast<uint32_t>(min(static_cast<uint64_t>(T_OUT), a.n_call - k0));
-        g.out0 = g.unit * a.n_call + k0;
-        g.f0 = 0;
+        g.skip = 0;
+        g.f0 = static_cast<int64_t>(g.unit * a.n_call + k0);
         g.u0 = 0;
         g.n_tile0 = (a.off0 + g.unit * a.S + k0) * D + i0;
     }
@@ -223,12 +229,16 @@ __device__ __forceinline__ float2 mix_exact(float2 v, double nd, double ratio, c
     return cmul_exact(v, make_float2(static_cast<float>(c), static_cast<float>(sn)));
 }
 
+// l_lo: local samples below it belong to an earlier launch (first tile of a launch only): they are neither
+// loaded nor stored, but every recurrence steps through their groups as if they were, so that the samples that
+// are wanted come out exactly as in a launch that covers the whole tile.
 template <int FMT, int D, int R, int NT, int LMAX, bool ALIGNED, bool FASTMIX>
-__device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
+__device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t l_lo, uint32_t n_dec,
                                             uint64_t n_tile0, float2 *__restrict__ X, int tid)
 {
     using Gm = FirGeom<D, R, NT, LMAX>;
     const int n_have = static_cast<int>(n_dec + lead);
+    const int n_skip = static_cast<int>(l_lo + lead); // raw-group-relative index of the first wanted sample
     const uint32_t n_groups = static_cast<uint32_t>(n_have + 3) / 4;
     // absolute index of raw group 0, sample 0, as an exact f64 (indices stay far below 2^53)
     const double base_d = __ull2double_rn(n_tile0 - lead);
@@ -253,9 +263,10 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
     // cf32 groups come from global memory (L2, after the bulk prefetch): keep the next group's loads in flight
     uint4 nlo = make_uint4(0, 0, 0, 0), nhi = make_uint4(0, 0, 0, 0);
     auto fetch = [&](uint32_t grp) {
-        nlo = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp);
-        nhi = make_uint4(0, 0, 0, 0);
-        if (static_cast<int>(4 * grp + 2) < n_have) nhi = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp + 1);
+        nlo = nhi = make_uint4(0, 0, 0, 0);
+        if (static_cast<int>(4 * grp + 1) >= n_skip) nlo = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp);
+        if (static_cast<int>(4 * grp + 2) < n_have && static_cast<int>(4 * grp + 3) >= n_skip)
+            nhi = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp + 1);
     };
     if (FMT == QD_FMT_CF32 && static_cast<uint32_t>(tid) < n_groups) fetch(tid);
     for (uint32_t grp = tid; grp < n_groups; grp += NT) {
@@ -272,7 +283,11 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
             w[0] = v.x, w[1] = v.y;
         }
         const int g4 = static_cast<int>(4 * grp);
-        const bool interior = g4 >= static_cast<int>(lead) && g4 + 3 < n_have;
+        if (g4 + 3 < n_skip) { // nothing wanted in this group: only the phasor recurrence moves on
+            if (FASTMIX && n_shift) ph_g = cmul_fast(ph_g, a.rot_step);
+            continue;
+        }
+        const bool interior = g4 >= n_skip && g4 + 3 < n_have;
         float2 v[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) v[i] = decode_in_group<FMT, !FASTMIX>(w, i, one);
@@ -313,14 +328,14 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
             } else {
 #pragma unroll
                 for (int i = 0; i < 4; i++)
-                    if (g4 + i >= static_cast<int>(lead) && g4 + i < n_have)
+                    if (g4 + i >= n_skip && g4 + i < n_have)
                         reinterpret_cast<float2 *>(xb + (i >> 1) * Gm::G * Gm::PITCH)[i & 1] = v[i];
             }
         } else {
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const int l = g4 + i - static_cast<int>(lead);
-                if (l < 0 || l >= static_cast<int>(n_dec)) continue;
+                if (l < static_cast<int>(l_lo) || l >= static_cast<int>(n_dec)) continue;
                 const uint32_t pr = (static_cast<uint32_t>(l) >> 1) & (Gm::DR / 2 - 1);
                 float4 *el = X4 + ((pr & 1) * Gm::G + (pr >> 1)) * Gm::PITCH + (static_cast<uint32_t>(l) >> Gm::LOG_DR);
                 reinterpret_cast<float2 *>(el)[l & 1] = v[i];
@@ -380,7 +395,7 @@ struct LeanParams {
 };
 
 template <class Gm, int STRIDE, bool MIX>
-__device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr, uint32_t n_dec, uint64_t n0,
+__device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr, uint32_t l_lo, uint32_t n_dec, uint64_t n0,
                                             const LeanParams &lp, float2 rstep, float4 *__restrict__ X4, int idx)
 {
     static_assert(STRIDE % Gm::G == 0, "a thread's groups stay in one row");
@@ -405,6 +420,18 @@ __device__ __forceinline__ void decode_lean(const FirArgs &a, uint32_t raw_addr,
     const float2 r1c = make_float2(a.rot[1].x, a.rot[1].x), r1s = make_float2(a.rot[1].y, a.rot[1].y);
     const float2 k2c = make_float2(a.rot2c, a.rot2c); // 2 cos(ratio)
     const float2 rsc = make_float2(rstep.x, rstep.x), rss = make_float2(rstep.y, rstep.y);
+    if (l_lo) {
+        // first tile of a launch that starts inside it: the groups below the first wanted sample are not there,
+        // but the phasor and the rounding-error fraction step through them exactly as the full tile's loop would
+        const uint32_t rp_first = raw_addr + 8u * (l_lo >> 2);
+        for (; rp < rp_first && rp < rp_end; rp += 8u * STRIDE, xb += STRIDE / Gm::G) {
+            if (MIX) {
+                const float2 gp = make_float2(-g.y, g.x);
+                g = fma2(gp, rss, mul2(g, rsc));
+                W += wstep;
+            }
+        }
+    }
 #pragma unroll 4
     for (; rp < rp_end; rp += 8u * STRIDE, xb += STRIDE / Gm::G) {
         uint2 v;
@@ -567,7 +594,7 @@ __device__ __forceinline__ void decode_cf32_copy(const uint8_t *gsrc, uint32_t n
 }
 
 template <int D, int R, int NT, int LMAX, bool MIX>
-__device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t n_dec,
+__device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t *raw, uint32_t lead, uint32_t l_lo, uint32_t n_dec,
                                                  uint64_t n_tile0, const LeanPhase *lp, const double2 *ttab,
                                                  float2 *__restrict__ X, int tid)
 {
@@ -580,7 +607,7 @@ __device__ __forceinline__ void decode_tile_lean(const FirArgs &a, const uint8_t
         q.g0 = make_float2(static_cast<float>(fma(ac, t.x, -__dmul_rn(as, t.y))), static_cast<float>(fma(ac, t.y, __dmul_rn(as, t.x))));
         q.m64k = lp->m64k, q.mk32 = lp->mk32, q.esc = lp->esc;
     }
-    decode_lean<FirGeom<D, R, NT, LMAX>, NT, MIX>(a, smem_u32(raw) + 8u * (lead >> 2), n_dec, n_tile0, q, a.rot_step,
+    decode_lean<FirGeom<D, R, NT, LMAX>, NT, MIX>(a, smem_u32(raw) + 8u * (lead >> 2), l_lo, n_dec, n_tile0, q, a.rot_step,
                                                          reinterpret_cast<float4 *>(X), tid);
 }
 
@@ -696,24 +723,26 @@ template <int D, int R, int NTG, int LMAX, bool EXACT, int LS>
 __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, const TileGeo &g, const float2 *__restrict__ X,
                                  int xidx, int tid)
 {
-    if (static_cast<uint32_t>(R * tid) < g.cnt) {
+    // slots [skip, cnt) of the tile are wanted; a thread takes part when any of its R slots is
+    if (static_cast<uint32_t>(R * tid) < g.cnt && static_cast<uint32_t>(R * tid + R) > g.skip) {
+        const int64_t q = g.f0 + static_cast<int64_t>(R * tid); // the thread's first slot as a flat output index
         // the unit's raw buffer ends at (unit_top0 + n_call)*D + L: later samples do not exist for
         // this read (filter.rs:68-71) and the ascending tap loop stops there
         int64_t s_lim; // samples from the thread's first one to the end of its unit's raw buffer
         if (a.contiguous && a.ncall_log2 >= 0) {
             // units tile the output stream and n_call is a power of two: the outputs left in the thread's unit
             // come from a mask, and raw_end - n_first = left * D + (L - i0)
-            const uint64_t q = g.f0 + static_cast<uint64_t>(R * tid);
-            const uint64_t left = a.n_call - (q & (a.n_call - 1));
+            const uint64_t qq = q < 0 ? 0 : static_cast<uint64_t>(q);
+            const uint64_t left = a.n_call - (qq & (a.n_call - 1)) + (qq - static_cast<uint64_t>(q));
             s_lim = static_cast<int64_t>(left * D + (a.L - (a.L - a.L / 2)));
         } else {
             uint64_t unit_top0;
             if (a.contiguous) {
                 // one division per tile (g.u0 = f0 / n_call); a thread's outputs start `rel` past that unit
-                uint64_t rel = g.f0 - g.u0 * a.n_call + static_cast<uint64_t>(R * tid);
+                int64_t rel = q - static_cast<int64_t>(g.u0 * a.n_call);
                 uint64_t un = g.u0;
-                while (rel >= a.n_call) { // the tile runs over one or more unit boundaries
-                    rel -= a.n_call;
+                while (rel >= static_cast<int64_t>(a.n_call)) { // the tile runs over one or more unit boundaries
+                    rel -= static_cast<int64_t>(a.n_call);
                     un++;
                 }
                 unit_top0 = a.off0 + un * a.n_call;
@@ -740,14 +769,20 @@ __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, 
         } else {
             fir_dynamic<D, R, NTG, LMAX, EXACT>(X, xidx, Q, Lrem, s_end, taps, one, acc);
         }
-        float2 *o = a.out + g.out0 + static_cast<uint64_t>(R * tid);
-        if (R % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
-    #pragma unroll
-            for (int r = 0; r < R; r += 2)
-                *reinterpret_cast<float4 *>(o + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
-        } else {
-    #pragma unroll
-            for (int r = 0; r < R; r++) o[r] = acc[r];
+        float2 *o = a.out + q;
+        if (q >= 0 && q + R <= static_cast<int64_t>(a.total_out)) {
+            if (R % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+#pragma unroll
+                for (int r = 0; r < R; r += 2)
+                    *reinterpret_cast<float4 *>(o + r) = make_float4(acc[r].x, acc[r].y, acc[r + 1].x, acc[r + 1].y);
+            } else {
+#pragma unroll
+                for (int r = 0; r < R; r++) o[r] = acc[r];
+            }
+        } else { // a launch that starts or ends inside the thread's slots
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (q + r >= 0 && q + r < static_cast<int64_t>(a.total_out)) o[r] = acc[r];
         }
     }
 }
@@ -788,7 +823,8 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     auto tile_phase = [&](const TileGeo &g) { // one spare lane, one tile ahead
-        lean_phase(a, g.n_tile0, static_cast<uint32_t>(g.cnt - 1) * D + a.L + 4, lphase);
+        // the span of a FULL tile, whatever part of it this launch wants: `ok` must not depend on the launch
+        lean_phase(a, g.n_tile0, static_cast<uint32_t>(Gm::T_TILE - 1) * D + a.L + 4, lphase);
     };
     if (lean_mix) {
         double c, s;
@@ -798,19 +834,22 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
     }
     __syncthreads();
 
-    // raw byte range of a tile, widened to 16-byte boundaries for the bulk copy
+    // raw byte range of a tile, widened to 16-byte boundaries for the bulk copy.  Local sample 0 (n_tile0) of a
+    // launch's first tile may lie before the launch's first wanted sample -- even before the resident range --
+    // so addresses are formed in integer arithmetic and only [l_lo, n_dec) is touched.
     auto issue = [&](const TileGeo &g) {
         const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + a.L;
         const uint64_t n_dec = min(span, a.src_end - g.n_tile0);
-        const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * pb;
-        const uint8_t *abeg = reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
-        const uintptr_t gend = reinterpret_cast<uintptr_t>(gbeg + n_dec * pb);
-        const uint32_t bytes = static_cast<uint32_t>(((gend + 15) & ~uintptr_t(15)) - reinterpret_cast<uintptr_t>(abeg));
+        const uintptr_t g0 = reinterpret_cast<uintptr_t>(a.src) + (g.n_tile0 - a.src_base) * pb; // wraps consistently
+        const uintptr_t org = g0 & ~uintptr_t(15);
+        const uintptr_t abeg = (g0 + static_cast<uint64_t>(g.skip) * D * pb) & ~uintptr_t(15);
+        const uintptr_t aend = (g0 + n_dec * pb + 15) & ~uintptr_t(15);
+        const uint32_t bytes = static_cast<uint32_t>(aend - abeg);
         if (staged) {
             mbar_expect_tx(&mbar[0], bytes);
-            bulk_g2s(raw0, abeg, bytes, &mbar[0]);
+            bulk_g2s(raw0 + (abeg - org), reinterpret_cast<const void *>(abeg), bytes, &mbar[0]);
         } else {
-            bulk_prefetch_l2(abeg, bytes); // cf32: the decode stage reads global memory; make it an L2 hit
+            bulk_prefetch_l2(reinterpret_cast<const void *>(abeg), bytes); // cf32: the decode stage reads global memory; make it an L2 hit
         }
     };
 
@@ -821,21 +860,21 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         const TileGeo g = tile_geo<D, Gm::T_TILE>(a, tile);
         const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + a.L;
         const uint32_t n_dec = static_cast<uint32_t>(min(span, a.src_end - g.n_tile0));
-        const uint8_t *gbeg = a.src + (g.n_tile0 - a.src_base) * pb;
-        const uint32_t lead = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(gbeg) & 15) / pb;
+        const uintptr_t gbeg = reinterpret_cast<uintptr_t>(a.src) + (g.n_tile0 - a.src_base) * pb;
+        const uint32_t lead = static_cast<uint32_t>(gbeg & 15) / pb;
+        const uint32_t l_lo = g.skip * D; // first wanted local sample (0 except in a launch's first tile)
 
         if (staged) mbar_wait(&mbar[0], static_cast<uint32_t>(it & 1));
 
         // ---- decode + mix once per sample, into the polyphase layout ------------------------------
         {
-            const uint8_t *raw = staged ? raw0
-                                        : reinterpret_cast<const uint8_t *>(reinterpret_cast<uintptr_t>(gbeg) & ~uintptr_t(15));
+            const uint8_t *raw = staged ? raw0 : reinterpret_cast<const uint8_t *>(gbeg & ~uintptr_t(15));
             if (!EXACT && lean && (lead & 3) == 0 && (!lean_mix || lphase->ok)) {
-                if (lean_mix) decode_tile_lean<D, R, NT, LMAX, true>(a, raw, lead, n_dec, g.n_tile0, lphase, ttab, X, tid);
-                else decode_tile_lean<D, R, NT, LMAX, false>(a, raw, lead, n_dec, g.n_tile0, lphase, ttab, X, tid);
-            } else if (!staged && a.n_shift == 0 && lead == 0) {
+                if (lean_mix) decode_tile_lean<D, R, NT, LMAX, true>(a, raw, lead, l_lo, n_dec, g.n_tile0, lphase, ttab, X, tid);
+                else decode_tile_lean<D, R, NT, LMAX, false>(a, raw, lead, l_lo, n_dec, g.n_tile0, lphase, ttab, X, tid);
+            } else if (!staged && a.n_shift == 0 && lead == 0 && l_lo == 0) {
                 decode_cf32_copy<Gm, NT>(raw, n_dec, X, tid);
-            } else if (EXACT && staged && (lead & 3) == 0) {
+            } else if (EXACT && staged && (lead & 3) == 0 && l_lo == 0) {
                 const uint32_t raw_addr = smem_u32(raw) + pb * lead;
                 float4 *X4 = reinterpret_cast<float4 *>(X);
                 switch (a.fmt) {
@@ -845,17 +884,17 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
                 }
             } else if ((lead & 3) == 0) {
                 switch (a.fmt) {
-                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                default: decode_tile<QD_FMT_CF32, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, l_lo, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, l_lo, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, l_lo, n_dec, g.n_tile0, X, tid); break;
+                default: decode_tile<QD_FMT_CF32, D, R, NT, LMAX, true, !EXACT>(a, raw, lead, l_lo, n_dec, g.n_tile0, X, tid); break;
                 }
             } else {
                 switch (a.fmt) {
-                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
-                default: decode_tile<QD_FMT_CF32, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS8: decode_tile<QD_FMT_CS8, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, l_lo, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CU8: decode_tile<QD_FMT_CU8, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, l_lo, n_dec, g.n_tile0, X, tid); break;
+                case QD_FMT_CS16: decode_tile<QD_FMT_CS16, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, l_lo, n_dec, g.n_tile0, X, tid); break;
+                default: decode_tile<QD_FMT_CF32, D, R, NT, LMAX, false, !EXACT>(a, raw, lead, l_lo, n_dec, g.n_tile0, X, tid); break;
                 }
             }
         }
@@ -1032,6 +1071,9 @@ static FastPlan fast_plan(const Chain &c, uint64_t unit_len, uint64_t stride, ui
         f.stream_top = true;
     } else {
         f.stream_top = top.T == 0 && stride != unit_len && n_units > 1;
+        // windows further apart than they are wide: a stream would also compute (and, for host sources, budget
+        // for) the gaps between them; evaluate the windows on their own when the per-unit kernel can
+        if (f.stream_top && stride > unit_len && unit_len % static_cast<uint64_t>(top.shape.R) == 0) f.stream_top = false;
         if (!f.stream_top && c.allow_tail && top.T > 0 && top.T <= 32 && top.T < unit_len && stride < unit_len && n_units > 1) {
             f.stream_top = true;
             f.stream_tail = true;
@@ -1071,7 +1113,9 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     a.n_call = n_call;
     a.S = S;
     a.n_units = n_units;
-    a.contiguous = (S == n_call || n_units == 1) ? 1 : 0;
+    // units that tile the output stream are filtered as ONE stream cut into absolute tiles; a thread's R outputs
+    // must then never straddle a unit boundary (off0 and n_call multiples of R)
+    a.contiguous = (n_units == 1 || (S == n_call && off0 % R == 0 && n_call % R == 0)) ? 1 : 0;
     a.ncall_log2 = -1;
     if (is_pow2(n_call))
         for (int b = 0; b < 64; b++)
@@ -1079,7 +1123,12 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     a.total_out = total_out;
     const uint64_t t_out = static_cast<uint64_t>(tile_outputs(static_cast<int>(D), static_cast<int>(R), lp.shape.NT, a.L == 40 ? 40 : 0)); // as FirGeom::T_TILE of the kernel launch_fir_dr picks
     a.tiles_per_unit = static_cast<uint32_t>((n_call + t_out - 1) / t_out);
-    a.n_tiles = a.contiguous ? (total_out + t_out - 1) / t_out : n_units * a.tiles_per_unit;
+    if (a.contiguous) { // absolute tile numbering: see FirArgs::tile_first
+        a.tile_first = off0 / t_out;
+        a.n_tiles = total_out ? (off0 + total_out - 1) / t_out - a.tile_first + 1 : 0;
+    } else {
+        a.n_tiles = n_units * a.tiles_per_unit;
+    }
     const uint64_t pb = pair_bytes(fmt);
     const uint64_t span_max = (t_out - 1) * D + a.L;
     a.raw_cap = fmt == QD_FMT_CF32 ? 0 : static_cast<uint32_t>(((span_max * pb + 15) / 16) * 16 + 32);
@@ -1172,10 +1221,13 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
     // segment size: everything at once when both ends are resident on the device, else bounded
     // staging buffers that are double buffered against the copies
     uint64_t seg_units = n_full;
-    const uint64_t raw_per_unit = std::max<uint64_t>(1, std::min(stride, unit_len) * mult * pb);
+    // a segment of nu units stages the raw range of (nu - 1) * stride + unit_len top-level samples, and a stream
+    // of the same length: both grow by `stride` per unit, also when the windows are further apart than wide
+    const uint64_t step = (stride && n_units > 1) ? stride : unit_len;
+    const uint64_t raw_per_unit = std::max<uint64_t>(1, step * mult * pb);
     if (!on_device) seg_units = std::max<uint64_t>(1, c.segment_bytes / raw_per_unit);
     if (!d_direct) {
-        const uint64_t per_unit_out = (f.stream_top ? std::min(stride, unit_len) : unit_len) * sizeof(float2) *
+        const uint64_t per_unit_out = (f.stream_top ? step : unit_len) * sizeof(float2) *
                                       (f.n_lp == 2 ? (1 + top.D) : 1);
         seg_units = std::min<uint64_t>(seg_units, std::max<uint64_t>(1, c.scratch_budget / 2 / std::max<uint64_t>(1, per_unit_out)));
     }

@@ -262,6 +262,8 @@ __global__ void gk_dft(FftArgs a)
 
 Chain::~Chain()
 {
+    for (qd_chain *s : shards) delete s; // a sharded handle owns one chain per device
+    shards.clear();
     if (src.fd >= 0) close(src.fd);
     src.fd = -1;
     if (!ctx) return; // description-only chain (qd_shard_plan): nothing lives on a device
@@ -286,6 +288,7 @@ Chain::~Chain()
         rel(pipe_out[j]);
         rel(pipe_idx[j]);
         rel(pipe_mag[j]);
+        rel(pipe_tail[j]);
         if (h_pin2[j]) cudaFreeHost(h_pin2[j]);
     }
     if (pipeline_ready) {
@@ -690,7 +693,8 @@ static int run_units_rawfft(Chain &c, uint64_t off0, uint64_t stride, uint64_t n
     const uint64_t pb = pair_bytes(s.format);
     const bool on_device = s.kind == QD_SRC_DEVICE_MEM;
     uint64_t seg_units = n_units;
-    if (!on_device) seg_units = std::max<uint64_t>(1, c.segment_bytes / std::max<uint64_t>(1, std::min(stride, W) * pb));
+    // a segment of nu windows stages (nu - 1) * stride + W samples: `stride` per window, also when stride > W
+    if (!on_device) seg_units = std::max<uint64_t>(1, c.segment_bytes / std::max<uint64_t>(1, ((stride && n_units > 1) ? stride : W) * pb));
     if (sink.space == QD_SPACE_HOST)
         seg_units = std::min<uint64_t>(seg_units, std::max<uint64_t>(1, c.scratch_budget / 2 / (W * 5)));
     seg_units = std::min(seg_units, n_units);

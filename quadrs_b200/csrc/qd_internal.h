@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdarg>
+#include <functional>
 #include <cstdint>
 #include <cstdio>
 #include <mutex>
@@ -12,6 +13,8 @@
 #include <vector>
 
 #include "../../include/quadrs_gpu.h"
+
+struct qd_chain;
 
 namespace qd {
 
@@ -89,6 +92,7 @@ struct DeviceCtx {
     double *d_sincos = nullptr; // 256 x {cos_hi, cos_lo, sin_hi, sin_lo}
     int16_t *d_sine_i16 = nullptr;
     int sm_count = 0;
+    std::vector<int> local_cpus; // CPUs on the GPU's NUMA node (sysfs local_cpulist of its PCI function); may be empty
 };
 int device_ctx(int device, DeviceCtx **out);
 
@@ -126,6 +130,9 @@ struct Chain {
     bool own_stream = false;
     int precision = QD_PRECISION_EXACT;
     std::mutex mu;
+    // qd_chain_create_sharded: the handle owns one complete chain per device and computes nothing itself
+    std::vector<qd_chain *> shards;
+    bool sharded() const { return !shards.empty(); }
 
     // device scratch (grown on demand, reused between calls)
     struct Buf {
@@ -176,6 +183,10 @@ struct Chain {
     int ensure(Buf &b, size_t bytes);
     int ensure_pinned(size_t bytes);
 };
+
+} // namespace qd
+struct qd_chain : qd::Chain {};
+namespace qd {
 
 // host-side cascade (exactly the reference's len()/read_at() count arithmetic)
 int chain_len(const Chain &c, uint64_t *len);
@@ -248,6 +259,21 @@ struct FftArgs {
 // graph[7] panic zone; thr[8]: smallest s with norm >= max.  false when min/max make that ill-defined.
 bool spark_thresholds(float mn, float mx, double thr[9]);
 int launch_stft_fast(Chain &c, const FftArgs &fa, uint64_t units, bool *handled);
+
+// ---------------------------------------------------------------- single-process multi-GPU (qd_multi.cu)
+// Runs fn(i, shard i) for every shard of a sharded chain, each on its own host thread bound to the CPUs local
+// to the shard's GPU; rc[i] / msg[i] receive each call's status and thread-local error text.
+void run_on_shards(Chain &c, const std::function<int(size_t, qd_chain *)> &fn, std::vector<int> &rc, std::vector<std::string> &msg);
+// status of the first failing shard in shard order (its message becomes the caller's qd_last_error), or QD_OK
+int first_shard_error(const std::vector<int> &rc, const std::vector<std::string> &msg, size_t *which);
+// [begin, end) of part i when n units are cut into parts contiguous ranges
+inline void shard_range(uint64_t n, size_t parts, size_t i, uint64_t *begin, uint64_t *end)
+{
+    *begin = static_cast<uint64_t>((static_cast<unsigned __int128>(n) * i) / parts);
+    *end = static_cast<uint64_t>((static_cast<unsigned __int128>(n) * (i + 1)) / parts);
+}
+void bind_thread_to_device_cpus(const DeviceCtx *ctx);
+std::vector<int> device_local_cpus(int device);
 
 int synth_fill(const qd_synth *p, int format, uint64_t first, uint64_t n, void *d_out, int device, cudaStream_t st);
 

@@ -26,7 +26,7 @@ def test_header_symbols_all_exported(Q):
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, missing
     assert declared == set(Q._lib.ABI_SYMBOLS), declared ^ set(Q._lib.ABI_SYMBOLS)
-    assert lib.qd_abi_version() == 1
+    assert lib.qd_abi_version() == 2
 
 
 def test_status_codes_shared_with_oracle(Q):

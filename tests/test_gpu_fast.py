@@ -438,3 +438,126 @@ def test_shards_and_pointers_at_awkward_alignments(Q):
         with pytest.raises(Q.QdError) as e:  # a device pointer in the middle of a sample is refused
             Q.Samples.from_device(buf.data_ptr() + 1, part.size, Q.CS8, 20_000_000)
         assert e.value.code == Q._lib.E_INVALID_ARG
+
+
+# ---------------------------------------------------------------- FAST results never depend on how a run is cut
+FAST_CUT_CASES = [
+    (O.CS8, 20_000_000, [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)]),    # lean loop, tiles of 508
+    (O.CS8, 20_000_000, [("shift", -9_999_999), ("lowpass", 1_000_000, 8, 40)]),   # near Nyquist
+    (O.CS8, 20_000_000, [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 56)]),    # run-time filter length
+    (O.CF32, 21_000_000, [("shift", 280_000), ("lowpass", 200_000, 32, 400)]),     # general FAST loop
+    (O.CS8, 20_000_000, [("shift", 700_000), ("shift", 800_000), ("lowpass", 1_000_000, 4, 40)]),
+]
+
+
+@pytest.mark.parametrize("fmt,rate,stages", FAST_CUT_CASES)
+def test_fast_output_is_independent_of_segments_and_shards(Q, fmt, rate, stages):
+    """shift.rs:49 makes the phase a function of the absolute index alone; the FAST kernel's tiles, anchors and
+    recurrences are numbered from absolute output 0, so host-path segments of any size, shards and the
+    device-resident path all produce the same bits."""
+    import torch
+
+    n = 1_500_000
+    pb = O.FORMAT_BYTES[fmt]
+    raw, _ = synth_raw(fmt, n, rate=rate)
+    d_raw = torch.from_numpy(raw).cuda()
+    dev = Q.Samples.from_device(d_raw.data_ptr(), raw.size, fmt, rate, keep=(d_raw,))
+    for st in stages:
+        dev = dev.shift(st[1]) if st[0] == "shift" else dev.lowpass(st[1], st[2], st[3])
+    dev = dev.with_precision(Q.FAST)
+    want, want_rc = dev.write_mem()
+    assert len(want) > 10 * 0x1000 or stages[-1][2] >= 32
+    # host path, two segment sizes (neither a multiple of the tile size)
+    for seg in (100_000, 1 << 20):
+        h = gpu_chain(raw, fmt, rate, stages, precision=Q.FAST)
+        h.set_option("segment_bytes", seg)
+        got, rc = h.write_mem()
+        assert rc == want_rc
+        assert_bit_equal(got, want, f"host path, segment_bytes {seg}")
+    # shards
+    for n_shards in (2, 3):
+        outs = []
+        for r in range(n_shards):
+            w = Q.shard_plan(fmt, rate, n, stages, Q.shard.SINK_WRITE, 0x1000, 0x1000, n_shards, r)
+            part = raw[w.first_sample * pb : (w.first_sample + w.n_samples) * pb]
+            g = gpu_chain(part, fmt, rate, stages, base=w.first_sample, total=n, precision=Q.FAST)
+            o, _ = g.write_mem(first_chunk=w.first_unit, max_chunks=w.n_units)
+            outs.append(o)
+        assert_bit_equal(np.concatenate(outs), want, f"{n_shards} shards")
+    # a read that starts in the middle of a tile and of a chunk: its untruncated part is the stream's
+    D, L = stages[-1][2], stages[-1][3]
+    T = -(-(L - L // 2) // D) - 1
+    for off, cnt in ((4096 + 130, 1000), (509, 2 * 508 + 4), (12, 3000)):
+        if off + cnt >= len(want):
+            continue
+        if cnt % 8:
+            cnt -= cnt % 8
+        got = dev.read_at(off, cnt)
+        chunk_end = (off // 0x1000 + 1) * 0x1000
+        keep = min(cnt - T, chunk_end - T - off)  # positions that are untruncated both in the read and in its write chunk
+        assert_bit_equal(got[:keep], want[off : off + keep], f"read_at({off}, {cnt})")
+
+
+def test_fast_sparkfft_is_independent_of_segments(Q):
+    n = 1_200_000
+    raw, _ = synth_raw(O.CS8, n)
+    st = [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)]
+    for W, S in ((64, 16), (64, 64), (16, 6)):
+        ref = None
+        for seg in (0, 70_000, 1 << 19):
+            g = gpu_chain(raw, O.CS8, 20_000_000, st, precision=Q.FAST)
+            if seg:
+                g.set_option("segment_bytes", seg)
+            idx, mag = g.spark_fft(W, S, (0.01, 3.0), want_mag=True)
+            if ref is None:
+                ref = (idx, mag)
+            else:
+                assert np.array_equal(idx, ref[0]), (W, S, seg)
+                assert_bit_equal(mag, ref[1], f"sparkfft {W}/{S} segment_bytes {seg}")
+
+
+def test_fast_full_size_config2_shards_and_host_path_bitwise(Q):
+    """2^30 cs8 samples in FAST arithmetic: 2- and 3-shard concatenations and the pipelined host path (two segment
+    sizes) equal the unsharded device-resident run in every bit."""
+    import torch
+
+    n = 2**30
+    fmt, rate = Q.CS8, 20_000_000
+    st = [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)]
+    synth = Q.make_synth(0x5EED0002, [(Q.tone_step(1.6e6, rate), 45, 0), (Q.tone_step(-4.1e6, rate), 30, 0),
+                                      (Q.tone_step(0.3e6, rate), 20, 3000)], 6)
+    d_in = torch.empty(2 * n, dtype=torch.uint8, device="cuda")
+    Q.synth_fill_device(synth, fmt, 0, n, d_in.data_ptr())
+    torch.cuda.synchronize()
+
+    def build(s):
+        return s.shift(1_500_000).lowpass(1_000_000, 8, 40).with_precision(Q.FAST)
+
+    chunks = 32767
+    d_out = torch.zeros(2 * chunks * 0x1000, dtype=torch.float32, device="cuda")
+    whole = build(Q.Samples.from_device(d_in.data_ptr(), 2 * n, fmt, rate, keep=(d_in,)))
+    got_n, _ = whole.write_into(0x1000, 0, chunks, d_out.data_ptr(), chunks * 0x1000, Q._lib.SPACE_DEVICE)
+    whole.synchronize()
+    assert got_n == chunks * 0x1000
+    for n_shards in (2, 3):
+        d_out2 = torch.zeros_like(d_out)
+        for r in range(n_shards):
+            p = Q.shard_plan(fmt, rate, n, st, Q.shard.SINK_WRITE, 0x1000, 0x1000, n_shards, r)
+            view = d_in[2 * p.first_sample : 2 * (p.first_sample + p.n_samples)]
+            g = build(Q.Samples.from_device(view.data_ptr(), view.numel(), fmt, rate, base_sample=p.first_sample,
+                                            total_samples=n, keep=(d_in,)))
+            nu = min(p.n_units, chunks - p.first_unit)
+            g.write_into(0x1000, p.first_unit, nu, d_out2.data_ptr() + 8 * p.first_unit * 0x1000, nu * 0x1000,
+                         Q._lib.SPACE_DEVICE)
+            g.synchronize()
+        assert torch.equal(d_out, d_out2), f"{n_shards} shards"
+    h_in = torch.empty(2 * n, dtype=torch.uint8, pin_memory=True)
+    h_in.copy_(d_in)
+    h_out = torch.empty(2 * chunks * 0x1000, dtype=torch.float32, pin_memory=True)
+    for seg in (32 << 20, 24_000_000):
+        h = build(Q.Samples.from_host_ptr(h_in.data_ptr(), 2 * n, fmt, rate, keep=(h_in,)))
+        h.set_option("segment_bytes", seg)
+        h_out.zero_()
+        h.write_into(0x1000, 0, chunks, h_out.data_ptr(), chunks * 0x1000, Q._lib.SPACE_HOST)
+        h.synchronize()
+        assert torch.equal(h_out, d_out.cpu()), f"host path, segment_bytes {seg}"
