@@ -1,20 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the quadrs IQ DSP hot path on B200, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload all|cfg1|cfg2|cfg2s|cfg3|cfg4|cfg5] [--impl reference]
 
-A "step" is one pass of the hot path over one batch of synthetic input.  The default workload is
-BASELINE.json configs[1]: synthetic cs8 (HackRF) at 20 MS/s, 2^30 samples per GPU, decode + shift +
-lowpass -power 20 -decimate 8, delivered as do_write's 0x1000-sample chunks.  With N GPUs the logical
-capture is N * 2^30 samples and rank r owns the r-th contiguous range of write chunks plus its halo
-(weak scaling; absolute sample indices drive phase and truncation; no data-path collective).
+A "step" is one pass of the hot path over one batch of synthetic input.  The headline workload is
+BASELINE.json configs[3], the metric's literal chain on its largest single-GPU configuration: synthetic cs16 at
+100 MS/s, 2^33 samples, shift | lowpass -power 400 -decimate 16 | sparkfft -width 128, sharded over the N GPUs by
+contiguous row ranges with halo (strong scaling: the capture stays 2^33 samples; absolute sample indices drive
+phase and truncation; no data-path collective).  With `--workload all` (the default) the same JSON line carries a
+`configs` map with the other BASELINE configurations measured the same way (config 1's chain at capture scale,
+config 2, config 2's input through sparkfft, config 3 at 2^30, config 5 as a resident 2^32-sample buffer
+processed at 4 absolute offsets), each a fixed per-GPU size (weak scaling).
 
-Rank 0 prints ONE JSON line.  `value` = input Msamples/s with the input resident in HBM, timed with
-CUDA events on the stream the kernels run on (max over ranks).  `e2e` = the same metric through the
-public API with HOST buffers: pinned host input -> H2D -> kernels -> D2H of the result, all inside the
-timed region.  `roofline` = algorithmic bytes of the dominant kernel / its device time, against the
-measured HBM peak of MEASURED_PEAKS.json.  `cpu_baseline` = the CPU oracle (a port of the reference
-algorithm; Rust cannot be built here) timed on a bounded sample of the same workload.
+Rank 0 prints ONE JSON line.  `value` = input Msamples/s with the input resident in HBM, timed with CUDA events
+on the stream the kernels run on (max over ranks).  `e2e` = the same metric through the public C ABI with HOST
+buffers: pinned host input -> H2D -> kernels -> D2H of the result inside the timed region; with N > 1 it is ONE
+process (rank 0) driving all N devices through qd_chain_create_sharded, the way the reference's single-process
+caller would.  `roofline` = algorithmic bytes / device time against the measured HBM peak of MEASURED_PEAKS.json,
+with the FP32 co-bound of the exact-order FIR / FFT stated.  `cpu_baseline` = the CPU oracle (a C port of the
+reference algorithm; Rust cannot be built here) timed on a bounded sample of the same workload; its output
+checksum over those units is compared with the GPU's (`parity_checked`).
 """
 from __future__ import annotations
 
@@ -33,52 +38,56 @@ sys.path.insert(0, str(ROOT / "tests"))
 
 CS8, CU8, CS16, CF32 = 1, 2, 3, 0
 PAIR = {CF32: 8, CS8: 2, CU8: 2, CS16: 4}
+FMT_NAME = {CF32: "cf32", CS8: "cs8", CU8: "cu8", CS16: "cs16"}
 
-# name -> description of one workload.  sink: ("write", chunk) or ("sparkfft", W, S, (lo, hi))
+# name -> one workload.  sink: ("write", chunk) or ("sparkfft", W, S, (lo, hi)).  samples: per GPU (weak) or of the
+# whole capture (strong).  passes: the resident buffer is processed at this many absolute offsets per step.
 WORKLOADS = {
+    # BASELINE.json configs[3] -- the headline
+    "cfg4": dict(
+        title="synthetic cs16 100 MS/s, 2^33 samples: shift 7000000 | lowpass -power 400 -decimate 16 2000000 | sparkfft -width 128 -range 0.5:50, sharded over the GPUs",
+        fmt=CS16, rate=100_000_000, samples=2**33, scaling="strong",
+        stages=[("shift", 7_000_000), ("lowpass", 2_000_000, 16, 800)], sink=("sparkfft", 128, 128, (0.5, 50.0)),
+        tones=[(7.3e6, 9000, 0), (6.2e6, 6000, 50_000), (-20e6, 4000, 0)], noise=1200, seed=0x5EED0004,
+        cpu_units=1536, ref_units_per_thread=96),
+    # BASELINE.json configs[0] (the reference's own example chain) at capture scale: overlapping windows
+    "cfg1": dict(
+        title="synthetic cf32 21 MS/s, 2^27 samples/GPU: shift 280000 | lowpass -power 200 -decimate 32 200000 | sparkfft -width 64 -stride 16 -range 0.01:3",
+        fmt=CF32, rate=21_000_000, samples=2**27, scaling="weak",
+        stages=[("shift", 280_000), ("lowpass", 200_000, 32, 400)], sink=("sparkfft", 64, 16, (0.01, 3.0)),
+        tones=[(-250e3, 6000, 2000), (-310e3, 6000, 2000), (3e6, 9000, 0)], noise=300, seed=0x5EED0001,
+        cpu_units=1024, ref_units_per_thread=128),
     # BASELINE.json configs[1]
     "cfg2": dict(
         title="synthetic cs8 20 MS/s, 2^30 samples/GPU: decode + shift 1500000 + lowpass -power 20 -decimate 8 1000000 | write",
-        fmt=CS8, rate=20_000_000, samples=2**30,
+        fmt=CS8, rate=20_000_000, samples=2**30, scaling="weak",
         stages=[("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)], sink=("write", 0x1000),
         tones=[(1.6e6, 45, 0), (-4.1e6, 30, 0), (0.3e6, 20, 3000)], noise=6, seed=0x5EED0002,
-        out_bytes_per_unit=0x1000 * 8, cpu_units=8192, ref_units_per_thread=512),
-    # BASELINE.json configs[3] (per-GPU shard of 2^30 samples by default; --samples overrides)
-    "cfg4": dict(
-        title="synthetic cs16 100 MS/s: shift 7000000 | lowpass -power 400 -decimate 16 2000000 | sparkfft -width 128 -range 0.5:50",
-        fmt=CS16, rate=100_000_000, samples=2**30,
-        stages=[("shift", 7_000_000), ("lowpass", 2_000_000, 16, 800)], sink=("sparkfft", 128, 128, (0.5, 50.0)),
-        tones=[(7.3e6, 9000, 0), (6.2e6, 6000, 50_000), (-20e6, 4000, 0)], noise=1200, seed=0x5EED0004,
-        out_bytes_per_unit=128, cpu_units=2048, ref_units_per_thread=96),
-    # BASELINE.json configs[4] shape
-    "cfg5": dict(
-        title="synthetic cf32 400 MS/s: lowpass -decimate 8 20000000 | lowpass -decimate 32 500000 | sparkfft -width 4 -stride 2 -range 0.001:0.01",
-        fmt=CF32, rate=400_000_000, samples=2**29,
-        stages=[("lowpass", 20_000_000, 8, 40), ("lowpass", 500_000, 32, 40)], sink=("sparkfft", 4, 2, (0.001, 0.01)),
-        tones=[(0.1e6, 160, 1_000_000), (90e6, 3000, 0)], noise=40, seed=0x5EED0005,
-        out_bytes_per_unit=4, cpu_units=4096, ref_units_per_thread=256),
+        cpu_units=2048, ref_units_per_thread=512),
     # configs[1]'s input through the metric's literal chain: shift + lowpass + sparkfft with overlapping windows
     "cfg2s": dict(
-        title="synthetic cs8 20 MS/s: shift 1500000 | lowpass -power 20 -decimate 8 1000000 | sparkfft -width 64 -stride 16 -range 0.01:3",
-        fmt=CS8, rate=20_000_000, samples=2**30,
+        title="synthetic cs8 20 MS/s, 2^30 samples/GPU: shift 1500000 | lowpass -power 20 -decimate 8 1000000 | sparkfft -width 64 -stride 16 -range 0.01:3",
+        fmt=CS8, rate=20_000_000, samples=2**30, scaling="weak",
         stages=[("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)], sink=("sparkfft", 64, 16, (0.01, 3.0)),
         tones=[(1.6e6, 45, 0), (-4.1e6, 30, 0), (0.3e6, 20, 3000)], noise=6, seed=0x5EED0002,
-        out_bytes_per_unit=64, cpu_units=8192, ref_units_per_thread=512),
-    # BASELINE.json configs[0] (the reference's own example chain) at capture scale: overlapping windows
-    "cfg1": dict(
-        title="synthetic cf32 21 MS/s: shift 280000 | lowpass -power 200 -decimate 32 200000 | sparkfft -width 64 -stride 16 -range 0.01:3",
-        fmt=CF32, rate=21_000_000, samples=2**27,
-        stages=[("shift", 280_000), ("lowpass", 200_000, 32, 400)], sink=("sparkfft", 64, 16, (0.01, 3.0)),
-        tones=[(-250e3, 6000, 2000), (-310e3, 6000, 2000), (3e6, 9000, 0)], noise=300, seed=0x5EED0001,
-        out_bytes_per_unit=64, cpu_units=2048, ref_units_per_thread=128),
-    # BASELINE.json configs[2] shape
+        cpu_units=8192, ref_units_per_thread=512),
+    # BASELINE.json configs[2]
     "cfg3": dict(
-        title="synthetic cu8 2.4 MS/s multi-tone: sparkfft -width 4096 -stride 1024 -range 2:500",
-        fmt=CU8, rate=2_400_000, samples=2**28,
+        title="synthetic cu8 2.4 MS/s multi-tone, 2^30 samples/GPU: sparkfft -width 4096 -stride 1024 -range 2:500",
+        fmt=CU8, rate=2_400_000, samples=2**30, scaling="weak",
         stages=[], sink=("sparkfft", 4096, 1024, (2.0, 500.0)),
         tones=[(-800e3, 40, 0), (-123_456, 30, 0), (300e3, 25, 0), (1_000_001, 20, 0)], noise=4, seed=0x5EED0003,
-        out_bytes_per_unit=4096, cpu_units=4096, ref_units_per_thread=256),
+        cpu_units=2048, ref_units_per_thread=256),
+    # BASELINE.json configs[4]: 2^34 samples as a resident 2^32-sample buffer processed at 4 absolute offsets
+    "cfg5": dict(
+        title="synthetic cf32 400 MS/s, 2^34 samples/GPU (resident 2^32-sample buffer at 4 absolute offsets): lowpass -decimate 8 20000000 | lowpass -decimate 32 500000 | sparkfft -width 4 -stride 2 -range 0.001:0.01",
+        fmt=CF32, rate=400_000_000, samples=2**32, passes=4, scaling="weak",
+        stages=[("lowpass", 20_000_000, 8, 40), ("lowpass", 500_000, 32, 40)], sink=("sparkfft", 4, 2, (0.001, 0.01)),
+        tones=[(0.1e6, 160, 1_000_000), (90e6, 3000, 0)], noise=40, seed=0x5EED0005,
+        cpu_units=4096, ref_units_per_thread=256),
 }
+HEADLINE = "cfg4"
+MAP_ORDER = ["cfg1", "cfg2", "cfg2s", "cfg3", "cfg5"]
 
 METRIC = "input Msamples/s through shift+lowpass+sparkfft"
 
@@ -89,8 +98,8 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--samples", type=int, default=0, help="samples per GPU (default: the workload's)")
+    ap.add_argument("--workload", default="all", choices=["all"] + sorted(WORKLOADS))
+    ap.add_argument("--samples", type=int, default=0, help="override the workload's sample count")
     ap.add_argument("--precision", default="auto", choices=["auto", "exact", "fast"])
     ap.add_argument("--segment-mb", type=int, default=0, help="host-path segment size in MiB (default: the library's)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -108,9 +117,38 @@ def unit_geometry(w):
     return w["sink"][1], w["sink"][2]
 
 
+def chain_geometry(w):
+    """-> (raw samples per top-level sample, raw samples one unit's read touches)"""
+    unit_len, _ = unit_geometry(w)
+    mult, need = 1, unit_len
+    for st in reversed(w["stages"]):
+        if st[0] == "lowpass":
+            need = need * st[2] + st[3]
+            mult *= st[2]
+    return mult, need
+
+
+def workload_config(name, w, samples_total_note):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": w["title"], "name": name, "format": FMT_NAME[w["fmt"]], "sample_rate": w["rate"],
+            "capture_samples": samples_total_note, "scaling": w["scaling"],
+            "l2": "inputs far larger than L2 (126 MB); no flush needed"}
+
+
 def make_oracle_synth(O, w):
-    scale = 1
-    return O.make_synth(w["seed"], [(O.tone_step(f, w["rate"]), a * scale, k) for f, a, k in w["tones"]], w["noise"])
+    return O.make_synth(w["seed"], [(O.tone_step(f, w["rate"]), a, k) for f, a, k in w["tones"]], w["noise"])
+
+
+def checksum_np(np, arr, w):
+    """The oracle's qo_timed_run checksum of the same units, from the GPU's output bytes."""
+    if w["sink"][0] == "write":
+        v = arr.view(np.uint32).reshape(-1, w["sink"][1], 2).astype(np.uint64)
+        wt = np.arange(1, w["sink"][1] + 1, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            return int(((v[:, :, 0] + (v[:, :, 1] << np.uint64(1))) * wt[None, :]).sum(dtype=np.uint64))
+    W = w["sink"][1]
+    v = arr.reshape(-1, W).astype(np.uint64)
+    return int((v * np.arange(1, W + 1, dtype=np.uint64)[None, :]).sum(dtype=np.uint64))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -241,22 +279,16 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm: the CPU oracle (port of the reference algorithm) on all host threads
 # ------------------------------------------------------------------------------------------------
-def run_reference(args, w):
+def run_reference(args, name, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return  # other ranks exit 0 without work
-    import numpy as np
-
     import oracle_lib as O
 
     threads = os.cpu_count() or 1
     unit_len, stride = unit_geometry(w)
-    mult, need = 1, unit_len
-    for st in reversed(w["stages"]):
-        if st[0] == "lowpass":
-            need = need * st[2] + st[3]
-            mult *= st[2]
-    units = min(threads * w["ref_units_per_thread"], 16384)  # bounded: at most 2^29 input samples per step for cfg2
+    mult, need = chain_geometry(w)
+    units = min(threads * w["ref_units_per_thread"], 16384)  # a bounded sample of the workload per step
     n_in = (units - 1) * stride * mult + need + 64
     raw = O.synth_fill(make_oracle_synth(O, w), w["fmt"], 0, n_in)
     sink = w["sink"]
@@ -273,15 +305,17 @@ def run_reference(args, w):
     total = sum(step() for _ in range(args.steps))
     ms = 1e3 * total / max(1, args.steps)
     value = samples_per_step / (ms * 1e-3) / 1e6
-    sample = f"{units} sink units = {samples_per_step} input samples per step, {threads} threads over disjoint unit ranges"
+    sample = (f"{units} sink units = {samples_per_step} input samples per step (the first units of the same synthetic "
+              f"capture), {threads} threads over disjoint unit ranges")
+    total_samples = (args.samples or w["samples"]) * w.get("passes", 1) * (1 if w["scaling"] == "strong" else args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["title"], "name": args.workload,
-                   "note": "CPU oracle: C port of the reference algorithm (lazy per-chunk pull, full-rate "
-                           "complex_convolve, per-sample f64 sin/cos); the Rust reference cannot be built here"},
-        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(name, w, total_samples),
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "CPU oracle: C port of the reference algorithm (lazy per-window pull, full-rate "
+                                 "complex_convolve, per-sample f64 sin/cos); the Rust reference cannot be built here"},
         "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -291,46 +325,65 @@ def run_reference(args, w):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def run_b200(args, w):
+class Ctx:
+    pass
+
+
+def fp32_cobound(w, precision_fast, sm_count, sm_mhz):
+    """FP32 co-bound: packed f32x2 instructions per input sample that the reference's arithmetic
+    needs at the very least -- FIR: one FFMA2 per complex MAC in FAST mode, FMUL2 + FFMA2 in the reference's exact
+    mul-then-add order; FFT (our radix-4 DIT with individually rounded operations): per point and radix-4 level
+    3 twiddle products of 3 packed instructions and 8 packed adds for 4 points, i.e. 4.25, plus ~4 for the
+    magnitude/threshold epilogue -- against the FMA pipe's 64 packed lanes per clock per SM."""
+    import math
+
+    macs, rate_div = 0.0, 1
+    for st in w["stages"]:
+        if st[0] == "lowpass":
+            rate_div *= st[2]
+            macs += st[3] / rate_div
+    instr = macs * (1 if precision_fast else 2)
+    fft = 0.0
+    if w["sink"][0] == "sparkfft":
+        W, S = w["sink"][1], w["sink"][2]
+        per_point = 4.25 * math.log(W, 4) + 4.0
+        fft = per_point * W / (S * rate_div)
+    total = instr + fft
+    if total <= 0:
+        return None
+    peak_instr = sm_count * 64 * sm_mhz * 1e6
+    return {"fir_complex_macs_per_sample": macs, "fir_packed_instr_per_sample": instr,
+            "fft_packed_instr_per_sample": fft, "ceiling_msamples_per_s": peak_instr / total / 1e6}
+
+
+def run_workload(cx, name, w, headline):
+    """Runs one workload on this rank; rank 0 gets the result dict (others get None)."""
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    import quadrs_b200 as Q
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; quadrs_b200 has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    affinity = bind_to_gpu_cpus(local)  # pinned host buffers (e2e) are first-touched on the GPU's NUMA node
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
+    Q, args = cx.Q, cx.args
+    rank, world, local, dev, stream = cx.rank, cx.world, cx.local, cx.dev, cx.stream
+    lib = Q._lib.lib()
     fmt, rate, pb = w["fmt"], w["rate"], PAIR[w["fmt"]]
-    per_gpu = args.samples or w["samples"]
-    total = per_gpu * world
+    passes = w.get("passes", 1)
+    samples = args.samples or w["samples"]
+    strong = w["scaling"] == "strong"
+    n_shards = world * passes
+    total = samples * passes * (1 if strong else world)  # the logical capture
     unit_len, stride = unit_geometry(w)
     sk = sink_kind(w)
-    plan = Q.shard_plan(fmt, rate, total, w["stages"], sk, unit_len, stride, world, rank)
-    n_units, first_unit = plan.n_units, plan.first_unit
-    n_in = plan.n_samples
+    mult, need = chain_geometry(w)
+    out_per_unit = unit_len * 8 if sk == 0 else unit_len
+    plans = [Q.shard_plan(fmt, rate, total, w["stages"], sk, unit_len, stride, n_shards, rank * passes + p)
+             for p in range(passes)]
+    n_in = max(p.n_samples for p in plans)
+    n_units = sum(p.n_units for p in plans)
 
-    # ---- synthetic input, generated in place on this GPU at its absolute sample range ----
-    d_in = torch.empty(n_in * pb, dtype=torch.uint8, device=dev)
+    # ---- synthetic input, generated in place on this GPU at the absolute sample range of its first pass ----
+    d_in = torch.empty(n_in * pb + 64, dtype=torch.uint8, device=dev)
     synth = Q.make_synth(w["seed"], [(Q.tone_step(f, rate), a, k) for f, a, k in w["tones"]], w["noise"])
-    # a non-default stream: the library's kernels, our CUDA events and the generator all run on it
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    Q.synth_fill_device(synth, fmt, plan.first_sample, n_in, d_in.data_ptr(), local, stream.cuda_stream)
+    Q.synth_fill_device(synth, fmt, plans[0].first_sample, n_in, d_in.data_ptr(), local, stream.cuda_stream)
     torch.cuda.synchronize()
 
     if args.precision == "exact":
@@ -338,222 +391,396 @@ def run_b200(args, w):
     elif args.precision == "fast":
         precision = Q.FAST
     else:  # FAST only where it meets the 1e-5 bar: cs8 / cf32 with a cf32 sink (tests/test_gpu_fast.py)
-        precision = Q.FAST if (fmt in (CS8, CF32) and sk == 0 and hasattr(Q, "FAST_READY")) else Q.EXACT
+        precision = Q.FAST if (fmt in (CS8, CF32) and sk == 0) else Q.EXACT
+    if precision == Q.FAST and fmt in (CU8, CS16):
+        precision = Q.EXACT
 
-    def build_chain(src, prec=None):
+    def build_chain(src, prec, on_stream=True):
         s = src
         for st in w["stages"]:
             s = s.shift(st[1]) if st[0] == "shift" else s.lowpass(st[1], st[2], st[3])
-        s = s.with_precision(precision if prec is None else prec).with_stream(stream.cuda_stream)
+        s = s.with_precision(prec)
+        if on_stream:
+            s = s.with_stream(stream.cuda_stream)
         if args.segment_mb:
             s.set_option("segment_bytes", args.segment_mb << 20)
         return s
 
-    dev_chain = build_chain(Q.Samples.from_device(d_in.data_ptr(), n_in * pb, fmt, rate, local,
-                                                  base_sample=plan.first_sample, total_samples=total, keep=(d_in,)))
-    out_bytes = n_units * w["out_bytes_per_unit"]
-    d_out = torch.empty(out_bytes + 64, dtype=torch.uint8, device=dev)
+    def device_chains(prec):
+        return [build_chain(Q.Samples.from_device(d_in.data_ptr(), p.n_samples * pb, fmt, rate, local,
+                                                  base_sample=p.first_sample, total_samples=total, keep=(d_in,)), prec)
+                for p in plans]
 
-    def run(chain, out_ptr, space):
+    d_out = torch.empty(n_units * out_per_unit + 64, dtype=torch.uint8, device=dev)
+    out_off = [0]
+    for p in plans:
+        out_off.append(out_off[-1] + p.n_units * out_per_unit)
+
+    def run_one(chain, p, out_ptr, space):
         if sk == 0:
-            n, _ = chain.write_into(unit_len, first_unit, n_units, out_ptr, n_units * unit_len, space)
+            n, _ = chain.write_into(unit_len, p.first_unit, p.n_units, out_ptr, p.n_units * unit_len, space)
             return n
-        lo_hi = w["sink"][3]
         if space == Q._lib.SPACE_DEVICE:
-            return chain.spark_fft_device(unit_len, stride, lo_hi, first_unit, n_units, out_ptr)
-        return chain.spark_fft_into(unit_len, stride, lo_hi, first_unit, n_units, out_ptr)
+            return chain.spark_fft_device(unit_len, stride, w["sink"][3], p.first_unit, p.n_units, out_ptr)
+        return chain.spark_fft_into(unit_len, stride, w["sink"][3], p.first_unit, p.n_units, out_ptr)
 
-    mult = 1
-    for st in w["stages"]:
-        if st[0] == "lowpass":
-            mult *= st[2]
+    def run_device(chains):
+        got = 0
+        for i, (c, p) in enumerate(zip(chains, plans)):
+            got += run_one(c, p, d_out.data_ptr() + out_off[i], Q._lib.SPACE_DEVICE)
+        return got
+
     samples_per_step = n_units * stride * mult  # input samples consumed by this rank's units (halo excluded)
+    steps = args.steps if headline else max(3, min(args.steps, 5))
+    warm = max(args.warmup, 3)
 
-    # ---- device-resident timing (`value`) ----
-    lib = Q._lib.lib()
-    for _ in range(max(args.warmup, 3)):
-        produced = run(dev_chain, d_out.data_ptr(), Q._lib.SPACE_DEVICE)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    dev_chain.profile(True)
-    launches0 = lib.qd_kernel_launches()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        run(dev_chain, d_out.data_ptr(), Q._lib.SPACE_DEVICE)
-    ev1.record(stream)
-    barrier()
-    ms_dev = ev0.elapsed_time(ev1) / args.steps
-    launches = lib.qd_kernel_launches() - launches0
-    regions, kern_ms, kern_name = dev_chain.profile_read()
-    dev_chain.profile(False)
-    clocks = sampler.stop() if rank == 0 else None
-
-    # the bit-exact arithmetic mode, timed the same way, when the headline ran in FAST mode
-    exact_ms = None
-    if precision == Q.FAST:
-        exact_chain = build_chain(Q.Samples.from_device(d_in.data_ptr(), n_in * pb, fmt, rate, local,
-                                                        base_sample=plan.first_sample, total_samples=total,
-                                                        keep=(d_in,)), Q.EXACT)
-        for _ in range(3):
-            run(exact_chain, d_out.data_ptr(), Q._lib.SPACE_DEVICE)
-        barrier()
+    def timed(chains, k):
+        for _ in range(warm):
+            produced = run_device(chains)
+        cx.barrier()
+        for c in chains:
+            c.profile(True)
+        l0 = lib.qd_kernel_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cx.barrier()
         e0.record(stream)
-        for _ in range(min(args.steps, 5)):
-            run(exact_chain, d_out.data_ptr(), Q._lib.SPACE_DEVICE)
+        for _ in range(k):
+            run_device(chains)
         e1.record(stream)
-        barrier()
-        exact_ms = e0.elapsed_time(e1) / min(args.steps, 5)
-        run(dev_chain, d_out.data_ptr(), Q._lib.SPACE_DEVICE)  # leave the FAST result in d_out for the e2e comparison
-        barrier()
+        cx.barrier()
+        ms = e0.elapsed_time(e1) / k
+        launches = lib.qd_kernel_launches() - l0
+        kern_ms, kern_name = 0.0, ""
+        for c in chains:  # the passes run back to back on one stream: their dominant regions add up
+            _, t, nm = c.profile_read()
+            kern_ms += t
+            kern_name = nm or kern_name
+            c.profile(False)
+        return ms, launches, kern_ms / k, kern_name, produced
 
-    # ---- end-to-end timing through host buffers (`e2e`) ----
+    chains = device_chains(precision)
+    sampler = ClockSampler(local) if (rank == 0 and headline) else None
+    if sampler:
+        sampler.start()
+    ms_dev, launches, kern_ms, kern_name, produced = timed(chains, steps)
+    clocks = sampler.stop() if sampler else None
+
+    exact_ms = None
+    if precision == Q.FAST:  # the bit-exact arithmetic mode, timed the same way
+        ex = device_chains(Q.EXACT)
+        exact_ms = timed(ex, min(steps, 5))[0]
+        del ex
+        run_device(chains)  # leave the FAST result in d_out for the comparisons below
+        torch.cuda.synchronize()
+
+    # ---- parity: the CPU oracle on the first units of rank 0's own input, checksum against the GPU's output ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle_lib as O
+
+        units = min(w["cpu_units"], plans[0].n_units)
+        n = min((units - 1) * stride * mult + need + 64, plans[0].n_samples)
+        raw = d_in[: n * pb].cpu().numpy()
+        kw = dict(width=w["sink"][1], stride=w["sink"][2], rng=w["sink"][3]) if sk == 1 else {}
+        secs, want_sum = O.timed_run(raw, fmt, rate, w["stages"], "write" if sk == 0 else "sparkfft", 0, units, 1, **kw)
+        exact_out = d_out
+        if precision == Q.FAST:  # bit-exactness is EXACT's property; FAST is within 1e-5 of it (tests/test_gpu_fast.py)
+            exact_out = torch.empty_like(d_out)
+            ex = device_chains(Q.EXACT)
+            run_one(ex[0], plans[0], exact_out.data_ptr(), Q._lib.SPACE_DEVICE)
+            ex[0].synchronize()
+        got_sum = checksum_np(np, exact_out[: units * out_per_unit].cpu().numpy(), w)
+        cpu = {"value": units * stride * mult / secs / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
+               "sample": f"first {units} sink units ({units * stride * mult} input samples) of the same input, {secs:.1f} s, "
+                         "1 thread (the reference hot path is single-threaded)",
+               "parity_checked": bool(got_sum == want_sum),
+               "parity": f"position-weighted checksum of the EXACT-mode GPU output over those {units} units "
+                         f"{'==' if got_sum == want_sum else '!='} the oracle's"}
+        del exact_out
+
+    # ---- end-to-end through host buffers: ONE process (rank 0) drives every device ----
     e2e = None
-    if not args.no_e2e:
-        h_in = torch.empty(n_in * pb, dtype=torch.uint8, pin_memory=True)
-        h_in.copy_(d_in)
-        h_out = torch.empty(out_bytes + 64, dtype=torch.uint8, pin_memory=True)
-        host_chain = build_chain(Q.Samples.from_host_ptr(h_in.data_ptr(), n_in * pb, fmt, rate, local,
-                                                         base_sample=plan.first_sample, total_samples=total,
-                                                         keep=(h_in,)))
-        e2e_steps = max(1, min(args.steps, 5))
-        for _ in range(2):
-            run(host_chain, h_out.data_ptr(), Q._lib.SPACE_HOST)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            run(host_chain, h_out.data_ptr(), Q._lib.SPACE_HOST)
-            host_chain.synchronize()
-        barrier()
-        ms_e2e = 1e3 * (time.perf_counter() - t0) / e2e_steps
-        # the host-path result is the device-path result
-        same = bool(torch.equal(h_out[:out_bytes], d_out[:out_bytes].cpu()))
-        e2e = {"ms": ms_e2e, "same_as_device_path": same, "steps": e2e_steps}
-        del h_in, h_out, host_chain
+    if not args.no_e2e and (headline or world == 1):
+        e2e = run_e2e(cx, name, w, plans, total, precision, build_chain, d_in, d_out, out_per_unit, n_units)
 
-    # ---- max over ranks ----
+    # ---- max / sum over ranks ----
     if world > 1:
-        t = torch.tensor([ms_dev, e2e["ms"] if e2e else 0.0, float(samples_per_step), float(launches),
-                          exact_ms or 0.0], dtype=torch.float64, device=dev)
-        tmax = t.clone()
+        t = torch.tensor([ms_dev, float(samples_per_step), float(launches), exact_ms or 0.0, kern_ms],
+                         dtype=torch.float64, device=dev)
+        tmax, tsum = t.clone(), t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms_dev, ms_e2e_max = tmax[0].item(), tmax[1].item()
-        exact_ms = tmax[4].item() or None
-        total_samples_step = tsum[2].item()
-        launches_all = int(tsum[3].item())
+        ms_dev, exact_ms, kern_ms = tmax[0].item(), (tmax[3].item() or None), tmax[4].item()
+        total_samples_step, launches_all = tsum[1].item(), int(tsum[2].item())
     else:
-        ms_e2e_max = e2e["ms"] if e2e else 0.0
-        total_samples_step = float(samples_per_step)
-        launches_all = int(launches)
+        total_samples_step, launches_all = float(samples_per_step), int(launches)
 
+    del chains, d_in, d_out
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+
+    peak, peak_src = cx.peak
+    # algorithmic bytes per GPU and step: input read once + final output written once (cf32 for write, u8 per bin for sparkfft)
+    alg_bytes = sum(p.n_samples for p in plans) * pb + n_units * out_per_unit
+    prec_name = "fast" if precision == Q.FAST else "exact"
+    traffic, traffic_src = None, None
+    ent = cx.traffic.get(f"{name}:{prec_name}:{samples}")
+    if ent:
+        traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    cob = fp32_cobound(w, precision == Q.FAST, cx.sm_count, sm_mhz)
+    value = total_samples_step / (ms_dev * 1e-3) / 1e6
+    achieved = alg_bytes / (ms_dev * 1e-3) / 1e9  # on the whole step's device time (every kernel of the chain)
+    hbm_ceiling = peak * 1e9 / (alg_bytes / samples_per_step) / 1e6  # Msamples/s per GPU at 100 % of the measured HBM peak
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src, "kernel": kern_name, "kernel_ms_per_step": kern_ms,
+            "kernel_frac": (alg_bytes / (kern_ms * 1e-3) / 1e9 / peak) if kern_ms > 0 else None,
+            "step_ms": ms_dev, "algorithmic_bytes_per_step": alg_bytes, "peak_source": peak_src,
+            "hbm_ceiling_msamples_per_s": hbm_ceiling}
+    if cob:
+        per_gpu = value / world
+        cob["min_hbm_fp32_ceiling_msamples_per_s"] = min(hbm_ceiling, cob["ceiling_msamples_per_s"])
+        cob["frac_of_min_ceiling"] = per_gpu / cob["min_hbm_fp32_ceiling_msamples_per_s"]
+        roof["fp32_cobound"] = cob
+    res = {"value": value, "unit": "Msamples/s", "ms_per_step": ms_dev, "steps": steps, "precision": prec_name,
+           "samples_per_gpu": samples * passes, "units_per_gpu": n_units, "gpu_launches": launches_all,
+           "scaling": w["scaling"], "roofline": roof, "clocks": clocks,
+           "config": workload_config(name, w, total)}
+    if exact_ms:
+        res["exact_mode"] = {"value": total_samples_step / (exact_ms * 1e-3) / 1e6, "unit": "Msamples/s",
+                             "ms_per_step": exact_ms,
+                             "note": "same workload in EXACT arithmetic (bit-identical to the CPU oracle); FAST is within "
+                                     "1e-5 of it (tests/test_gpu_fast.py::test_fast_mode_full_size_config2_against_exact)"}
+    if e2e:
+        res["e2e"] = e2e
+    if cpu:
+        res["cpu_baseline"] = cpu
+        res["parity_checked"] = cpu["parity_checked"]
+    return res
+
+
+def run_e2e(cx, name, w, plans, total, precision, build_chain, d_in, d_out, out_per_unit, n_units_rank):
+    """Pinned host capture -> H2D -> kernels -> D2H of the result, inside the timed region, through the C ABI.  With
+    several GPUs rank 0 alone drives all of them with one sharded chain (the other ranks wait at a CPU barrier)."""
+    import torch
+
+    Q, args = cx.Q, cx.args
+    rank, world, local, dev, stream = cx.rank, cx.world, cx.local, cx.dev, cx.stream
+    fmt, rate, pb = w["fmt"], w["rate"], PAIR[w["fmt"]]
+    passes = w.get("passes", 1)
+    unit_len, stride = unit_geometry(w)
+    sk = sink_kind(w)
+    mult, _ = chain_geometry(w)
+    res = None
     if rank == 0:
-        peaks_path = ROOT / "MEASURED_PEAKS.json"
-        if peaks_path.exists():
-            peak, peak_src = json.loads(peaks_path.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        if world == 1:
+            # the capture of every pass is this rank's resident range
+            n_host = max(p.n_samples for p in plans)
+            h_in = cx.pinned_in(n_host * pb)
+            h_in.copy_(d_in[: n_host * pb])
+            jobs = [(p.first_sample, p.n_samples, p.first_unit, p.n_units) for p in plans]
+            devices = None
         else:
-            peak, peak_src = 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
-        # algorithmic bytes: input read once + final output written once (cf32 for write, u8 per bin for sparkfft)
-        alg_bytes = n_in * pb + (produced * 8 if sk == 0 else n_units * unit_len)
-        traffic, traffic_src = None, None
-        tpath = ROOT / "profiles" / "traffic.json"
-        if tpath.exists():
-            ent = json.loads(tpath.read_text()).get(f"{args.workload}:{'fast' if precision == Q.FAST else 'exact'}:{per_gpu}")
-            if ent:
-                traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
-        # FP32 co-bound of the FIR: complex MACs per input sample, each one packed FFMA2 in FAST
-        # mode and two packed instructions (FMUL2 + FFMA2) in the reference's exact mul-then-add order; the FMA
-        # pipe retires 64 packed lanes per clock per SM
-        macs, rate_div = 0.0, 1
-        for st in w["stages"]:
-            if st[0] == "lowpass":
-                rate_div *= st[2]
-                macs += st[3] / rate_div
-        fir = None
-        if macs:
-            instr = macs * (1 if precision == Q.FAST else 2)
-            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-            peak_instr = torch.cuda.get_device_properties(dev).multi_processor_count * 64 * sm_mhz * 1e6
-            fir = {"complex_macs_per_sample": macs, "packed_instr_per_sample": instr,
-                   "ceiling_msamples_per_s": peak_instr / instr / 1e6}
-        kern_avg_ms = kern_ms / max(1, args.steps)  # device ms per step of the dominant kernel (CUDA events around its launches)
-        achieved = alg_bytes / (kern_avg_ms * 1e-3) / 1e9 if kern_avg_ms > 0 else None
-        value = total_samples_step / (ms_dev * 1e-3) / 1e6
+            # the whole capture in host memory (generated in pieces on this GPU), all units, all devices
+            whole = Q.shard_plan(fmt, rate, total, w["stages"], sk, unit_len, stride, 1, 0)
+            n_host = whole.n_samples
+            h_in = cx.pinned_in(n_host * pb)
+            synth = Q.make_synth(w["seed"], [(Q.tone_step(f, rate), a, k) for f, a, k in w["tones"]], w["noise"])
+            piece = 1 << 30
+            tmp = torch.empty(piece * pb, dtype=torch.uint8, device=dev)
+            for s0 in range(0, n_host, piece):
+                n = min(piece, n_host - s0)
+                Q.synth_fill_device(synth, fmt, whole.first_sample + s0, n, tmp.data_ptr(), local, stream.cuda_stream)
+                stream.synchronize()
+                h_in[s0 * pb : (s0 + n) * pb].copy_(tmp[: n * pb])
+            del tmp
+            jobs = [(whole.first_sample, whole.n_samples, whole.first_unit, whole.n_units)]
+            devices = list(range(world))
+        units_all = sum(j[3] for j in jobs)
+        h_out = cx.pinned_out(units_all * out_per_unit)
+        chains = []
+        for first_sample, n_samples, _, _ in jobs:
+            src = Q.Samples.from_host_ptr(h_in.data_ptr(), n_samples * pb, fmt, rate, local if devices is None else devices,
+                                          base_sample=first_sample, total_samples=total, keep=(h_in,))
+            chains.append(build_chain(src, precision, on_stream=devices is None))
+
+        def step():
+            off = 0
+            for c, (_, _, first_unit, nu) in zip(chains, jobs):
+                if sk == 0:
+                    c.write_into(unit_len, first_unit, nu, h_out.data_ptr() + off, nu * unit_len, Q._lib.SPACE_HOST)
+                else:
+                    c.spark_fft_into(unit_len, stride, w["sink"][3], first_unit, nu, h_out.data_ptr() + off)
+                off += nu * out_per_unit
+            for c in chains:
+                c.synchronize()
+
+        k = 3 if passes == 1 else 2
+        step()
+        if passes == 1:
+            step()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            step()
+        ms = 1e3 * (time.perf_counter() - t0) / k
+        # the host-path result is the device-path result (rank 0's own units)
+        nb = n_units_rank * out_per_unit
+        same = bool(torch.equal(h_out[:nb], d_out[:nb].cpu()))
+        samples_step = units_all * stride * mult
+        res = {"value": samples_step / (ms * 1e-3) / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": sum(j[1] for j in jobs) * pb, "d2h_bytes_per_step": units_all * out_per_unit,
+               "ms_per_step": ms, "steps": k, "same_as_device_path": same,
+               "driver": "one host process" + (f", one sharded chain over {world} devices (qd_chain_create_sharded)"
+                                                if devices else "")}
+        del chains
+    cx.cpu_barrier()
+    return res
+
+
+def host_copy_peak(cx):
+    """Aggregate pinned-host -> device copy bandwidth with every GPU copying at once and no kernel running: the
+    denominator of the end-to-end number at N GPUs (rank 0 drives all devices, as the e2e leg does)."""
+    import torch
+
+    if cx.rank != 0:
+        cx.cpu_barrier()
+        return None
+    n = 1 << 30
+    h = cx.pinned_in(n * cx.world)
+    bufs, streams = [], []
+    for d in range(cx.world):
+        with torch.cuda.device(d):
+            bufs.append(torch.empty(n, dtype=torch.uint8, device=f"cuda:{d}"))
+            streams.append(torch.cuda.Stream(device=d))
+
+    def once():
+        for d in range(cx.world):
+            with torch.cuda.stream(streams[d]):
+                bufs[d].copy_(h[d * n : (d + 1) * n], non_blocking=True)
+        for s in streams:
+            s.synchronize()
+
+    once()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        once()
+    dt = (time.perf_counter() - t0) / 3
+    del bufs
+    cx.cpu_barrier()
+    return {"h2d_gb_per_s": cx.world * n / dt / 1e9, "devices": cx.world,
+            "how": "1 GiB per device from one pinned buffer, all devices at once, 3 repeats, wall clock"}
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    import quadrs_b200 as Q
+
+    cx = Ctx()
+    cx.Q, cx.args = Q, args
+    cx.rank = int(os.environ.get("RANK", "0"))
+    cx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; quadrs_b200 has no CPU fallback")
+    torch.cuda.set_device(cx.local)
+    cx.dev = torch.device("cuda", cx.local)
+    # no CPU binding here: rank 0's library worker threads bind themselves to each GPU's local CPUs (qd_multi.cu)
+    gloo = None
+    if cx.world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=cx.dev)
+        gloo = dist.new_group(backend="gloo")  # CPU-side waits while rank 0 drives every device (e2e leg)
+
+    def barrier():
+        if cx.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def cpu_barrier():
+        if cx.world > 1:
+            dist.barrier(group=gloo)
+
+    cx.barrier, cx.cpu_barrier = barrier, cpu_barrier
+    cx.stream = torch.cuda.Stream(device=cx.dev)  # the library's kernels, our CUDA events and the generator all run on it
+    torch.cuda.set_stream(cx.stream)
+    cx.sm_count = torch.cuda.get_device_properties(cx.dev).multi_processor_count
+    pin = {}
+
+    def pinned(kind, nbytes):  # one pinned buffer per direction, grown on demand (pinning tens of GiB is slow)
+        t = pin.get(kind)
+        if t is None or t.numel() < nbytes:
+            pin[kind] = None
+            t = torch.empty(nbytes + (16 << 20), dtype=torch.uint8, pin_memory=True)  # slack: later workloads reuse it
+            pin[kind] = t
+        return t[:nbytes]
+
+    cx.pinned_in = lambda n: pinned("in", n)
+    cx.pinned_out = lambda n: pinned("out", n + 64)
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        cx.peak = (json.loads(peaks_path.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)")
+    else:
+        cx.peak = (6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)")
+    tpath = ROOT / "profiles" / "traffic.json"
+    cx.traffic = json.loads(tpath.read_text()) if tpath.exists() else {}
+
+    head_name = HEADLINE if args.workload == "all" else args.workload
+    t_start = time.time()
+    head = run_workload(cx, head_name, WORKLOADS[head_name], True)
+    others = {}
+    if args.workload == "all":
+        for nm in MAP_ORDER:
+            try:
+                r = run_workload(cx, nm, WORKLOADS[nm], False)
+            except Exception as e:  # a failing side workload must not cost the headline
+                r = {"error": f"{type(e).__name__}: {e}"}
+            if cx.rank == 0:
+                others[nm] = r
+    copy_peak = host_copy_peak(cx) if (cx.world > 1 and not args.no_e2e) else None
+
+    if cx.rank == 0:
+        w = WORKLOADS[head_name]
         line = {
-            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": w["title"], "name": args.workload, "samples_per_gpu": per_gpu,
-                       "capture_samples": total, "units_per_gpu": n_units, "input_bytes_per_gpu": n_in * pb,
-                       "precision": "fast" if precision == Q.FAST else "exact",
-                       "l2": "inputs larger than L2 (no flush needed)" if n_in * pb > 256 * 2**20 else "input smaller than 2x L2",
-                       "sharding": f"{world} contiguous unit ranges with halo, absolute indices, no collective",
-                       "rank_cpu_affinity": affinity},
-            "clocks": clocks,
-            "gpu_launches": launches_all,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": kern_name,
-                         "kernel_ms_per_step": kern_avg_ms, "algorithmic_bytes_per_step": alg_bytes,
-                         "peak_source": peak_src, "fir_fp32_cobound": fir},
+            "metric": METRIC, "value": head["value"], "unit": "Msamples/s", "n_gpus": cx.world, "steps": head["steps"],
+            "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": head["config"],
+            "run": {"precision": head["precision"], "samples_per_gpu": head["samples_per_gpu"],
+                    "units_per_gpu": head["units_per_gpu"],
+                    "sharding": f"{cx.world} contiguous unit ranges with halo, absolute indices, no collective",
+                    "wall_s": round(time.time() - t_start, 1)},
+            "clocks": head["clocks"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
         }
-        if fir:
-            fir["frac_of_ceiling"] = (value / world) / fir["ceiling_msamples_per_s"]
-        if exact_ms:
-            line["exact_mode"] = {"value": total_samples_step / (exact_ms * 1e-3) / 1e6, "unit": "Msamples/s",
-                                  "ms_per_step": exact_ms,
-                                  "note": "same workload in EXACT arithmetic (bit-identical to the CPU oracle); the "
-                                          "headline FAST mode is within 1e-5 of it on this workload "
-                                          "(tests/test_gpu_fast.py::test_fast_mode_full_size_config2_against_exact)"}
-        if e2e:
-            line["e2e"] = {"value": total_samples_step / (ms_e2e_max * 1e-3) / 1e6, "unit": "Msamples/s",
-                           "h2d_bytes_per_step": n_in * pb, "d2h_bytes_per_step": out_bytes,
-                           "ms_per_step": ms_e2e_max, "same_as_device_path": e2e["same_as_device_path"]}
-        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is reported at N = 1 only
-            line["cpu_baseline"] = cpu_baseline(w, d_in, plan, pb)
+        for k in ("exact_mode", "e2e", "cpu_baseline", "parity_checked"):
+            if k in head:
+                line[k] = head[k]
+        if copy_peak:
+            line["host_copy_peak"] = copy_peak
+            if "e2e" in line:
+                bps = line["e2e"]["h2d_bytes_per_step"] / (line["e2e"]["ms_per_step"] * 1e-3) / 1e9
+                line["e2e"]["h2d_gb_per_s"] = bps
+                line["e2e"]["frac_of_host_copy_peak"] = bps / copy_peak["h2d_gb_per_s"]
+        if others:
+            for r in others.values():
+                if r:
+                    r.pop("clocks", None)
+            line["configs"] = others
         print(json.dumps(line), flush=True)
-    if world > 1:
+    if cx.world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def cpu_baseline(w, d_in, plan, pb):
-    """The oracle (a port of the reference algorithm), 1 thread as the reference runs, on the first
-    cpu_units sink units of rank 0's own input bytes."""
-    import oracle_lib as O
-
-    unit_len, stride = unit_geometry(w)
-    mult, need = 1, unit_len
-    for st in reversed(w["stages"]):
-        if st[0] == "lowpass":
-            need = need * st[2] + st[3]
-            mult *= st[2]
-    units = min(w["cpu_units"], plan.n_units)
-    n = min((units - 1) * stride * mult + need + 64, plan.n_samples)
-    raw = d_in[: n * pb].cpu().numpy()
-    sink = w["sink"]
-    kw = dict(width=sink[1], stride=sink[2], rng=sink[3]) if sink[0] == "sparkfft" else {}
-    # rank 0 of a sharded run starts at sample 0, so unit indices are the shard's own
-    secs, _ = O.timed_run(raw, w["fmt"], w["rate"], w["stages"], "write" if sink[0] == "write" else "sparkfft",
-                          0, units, 1, **kw)
-    samples = units * stride * mult
-    return {"value": samples / secs / 1e6, "unit": "Msamples/s", "cores": 1, "kind": "port",
-            "sample": f"first {units} sink units ({samples} input samples) of the same input, {secs:.1f} s, 1 thread "
-                      "(the reference hot path is single-threaded)"}
-
-
 def main():
     args = parse_args()
-    w = WORKLOADS[args.workload]
     if args.impl == "reference":
-        run_reference(args, w)
+        name = HEADLINE if args.workload == "all" else args.workload
+        run_reference(args, name, WORKLOADS[name])
     else:
-        run_b200(args, w)
+        run_b200(args)
 
 
 if __name__ == "__main__":

@@ -1087,11 +1087,11 @@ static void *job_thread(void *arg)
             uint64_t n = 0;
             int rc = qo_write_mem(s, 0x1000, sl->first + c, 1, out, 0x1000, &n);
             if (rc != QO_OK && rc != QO_E_WRITE_SHORT) sl->rc = rc;
-            for (uint64_t i = 0; i < n; i++) {
+            for (uint64_t i = 0; i < n; i++) { /* position-weighted, so that swapped samples do not cancel */
                 uint32_t a, b;
                 memcpy(&a, &out[i].re, 4);
                 memcpy(&b, &out[i].im, 4);
-                sum += a + ((uint64_t)b << 1);
+                sum += (a + ((uint64_t)b << 1)) * (i + 1);
             }
         }
         free(out);
@@ -1104,7 +1104,7 @@ static void *job_thread(void *arg)
             int rc = qo_spark_fft(s, W, job->stride, job->has_range, job->min, job->has_range, job->max,
                                   sl->first + r, want, idx, NULL, &got);
             if (rc != QO_OK) sl->rc = rc;
-            for (uint64_t i = 0; i < got * W; i++) sum += idx[i];
+            for (uint64_t i = 0; i < got * W; i++) sum += (uint64_t)idx[i] * (i % W + 1); /* weighted by the bin */
         }
         free(idx);
     }
