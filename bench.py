@@ -85,6 +85,17 @@ WORKLOADS = {
         stages=[("lowpass", 20_000_000, 8, 40), ("lowpass", 500_000, 32, 40)], sink=("sparkfft", 4, 2, (0.001, 0.01)),
         tones=[(0.1e6, 160, 1_000_000), (90e6, 3000, 0)], noise=40, seed=0x5EED0005,
         cpu_units=4096, ref_units_per_thread=256),
+    # ---- kernel experiments (not part of the default line): the long filter alone, and the mixer alone ----
+    "x_fir16": dict(
+        title="experiment: cf32, lowpass -power 400 -decimate 16 | sparkfft -width 128 (config 4's filter without its decode + shift)",
+        fmt=CF32, rate=100_000_000, samples=2**28, scaling="weak",
+        stages=[("lowpass", 2_000_000, 16, 800)], sink=("sparkfft", 128, 128, (0.5, 50.0)),
+        tones=[(7.3e6, 9000, 0), (6.2e6, 6000, 50_000)], noise=1200, seed=0x5EED0014, cpu_units=256, ref_units_per_thread=16),
+    "x_mix16": dict(
+        title="experiment: cs16, shift | lowpass -power 8 -decimate 16 | sparkfft -width 128 (config 4's decode + shift with a short filter)",
+        fmt=CS16, rate=100_000_000, samples=2**28, scaling="weak",
+        stages=[("shift", 7_000_000), ("lowpass", 2_000_000, 16, 16)], sink=("sparkfft", 128, 128, (0.5, 50.0)),
+        tones=[(7.3e6, 9000, 0), (6.2e6, 6000, 50_000)], noise=1200, seed=0x5EED0024, cpu_units=256, ref_units_per_thread=16),
 }
 HEADLINE = "cfg4"
 MAP_ORDER = ["cfg1", "cfg2", "cfg2s", "cfg3", "cfg5"]

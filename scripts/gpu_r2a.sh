@@ -24,5 +24,9 @@ for wl in cfg4 cfg1 cfg5; do
   python bench.py --workload $wl --samples $S $B > $O/r2a_plain2_$wl.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:'fk_fir|fk_tail|fk_stft' -s $SK -c $CN -f -o $O/r2a_full_$wl \
       python bench.py --workload $wl --samples $S $B > $O/r2a_ncuf_$wl.log 2>&1
+  # summaries are made here: the reports themselves are too large to travel back (64 MiB limit)
+  python scripts/ncu_summary.py $O/r2a_full_$wl.ncu-rep --stalls --hot > $O/r2a_full_${wl}_summary.txt 2>&1
+  ncu -i $O/r2a_full_$wl.ncu-rep --page source --csv --print-source sass 2>/dev/null | cut -d, -f1-6,31-64 | gzip -9 > $O/r2a_full_${wl}_source.csv.gz
+  rm -f $O/r2a_full_$wl.ncu-rep
 done
 ls -la $O | tail -30
