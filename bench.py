@@ -113,6 +113,7 @@ def parse_args():
     ap.add_argument("--samples", type=int, default=0, help="override the workload's sample count")
     ap.add_argument("--precision", default="auto", choices=["auto", "exact", "fast"])
     ap.add_argument("--segment-mb", type=int, default=0, help="host-path segment size in MiB (default: the library's)")
+    ap.add_argument("--opt", action="append", default=[], help="chain option key=value (experiments)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -415,6 +416,9 @@ def run_workload(cx, name, w, headline):
             s = s.with_stream(stream.cuda_stream)
         if args.segment_mb:
             s.set_option("segment_bytes", args.segment_mb << 20)
+        for kv in args.opt:
+            k, v = kv.split("=")
+            s.set_option(k, int(v))
         return s
 
     def device_chains(prec):

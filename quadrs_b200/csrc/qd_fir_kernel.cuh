@@ -760,105 +760,173 @@ __device__ __forceinline__ void fir_static(const float2 *__restrict__ X, int tid
 }
 
 // Run-time filter length.  Unit (b, r) = sample block b of the thread applied to its output r with tap block
-// q = b - r; it exists for 0 <= q < Q and is whole for q < Qf = L / D.  Blocks R-1 <= b < Qf carry a whole tap block
-// for every output: they run as an unrolled body of R blocks whose taps come from the constant bank through
-// UNIFORM registers (the trip count and every tap index depend on kernel parameters only: LDCU, one load per
-// tap and R-block body, no per-thread constant loads) and broadcast into the packed multiplies, with the next
-// block's samples loaded while the current block is applied.  A thread whose unit ends early (the zero-truncated
-// tail of a read, filter.rs:68-71) stays in the loop with its accumulator updates predicated off block by block;
-// if its last block is a partial one it is applied afterwards (nothing follows it in that thread's sums).
-// snap_blk (nullable): output r's accumulator is copied to snap[r] right before block snap_blk[r] of the thread is
+// q = b - r; it exists for 0 <= q < Q and is whole for q < Qf = L / D.  Every block number, tap index and trip count
+// below is a function of kernel parameters alone, so the taps come from the constant bank through UNIFORM
+// registers (LDCU, four taps per load, broadcast into the packed multiplies: no per-thread constant loads) -- the
+// CPU-side test tests/test_sass.py checks that ptxas keeps it that way.  Blocks R-1 <= b < Qf carry a whole tap
+// block for every output: one block per iteration, the next block's samples in flight while this one is applied.
+// The few blocks before and after run the same way with the units that exist.  A thread whose unit ends early
+// (the zero-truncated tail of a read, filter.rs:68-71) stays in the loops with its accumulator updates predicated
+// off block by block; if its last block is a partial one it is applied afterwards (nothing follows it in that
+// thread's sums).
+// snap_blk (SNAP): output r's accumulator is copied to snap[r] right before block snap_blk[r] of the thread is
 // applied (see FirArgs::tail_out); the caller completes a snapshot that ends inside that block.
-template <int D, int R, int NT, int LMAX, bool EXACT>
+template <int D, int R, int NT, int LMAX, bool EXACT, bool SNAP = false>
 __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int tid, int Q, int Lrem, int s_end,
                                             const FirTaps &taps, float2 one, float2 (&acc)[R], const int *snap_blk = nullptr,
                                             float2 *snap = nullptr)
 {
-    auto take = [&](int blk) { // uniform branch: only stream launches that feed overlapping windows carry snapshots
-        if (snap_blk) {
+    auto take = [&](int blk) { // only stream launches that feed overlapping windows carry snapshots
+        if constexpr (SNAP) {
 #pragma unroll
             for (int r = 0; r < R; r++)
                 if (snap_blk[r] == blk) snap[r] = acc[r];
         }
     };
     // s_end: the thread's samples s >= s_end do not exist for this read; untruncated threads pass (R-1)*D + L
-    const int NB = R - 1 + Q;
-    const int Qf = Lrem == D ? Q : Q - 1; // whole tap blocks
-    const int nfull = s_end / D;          // the thread's blocks b < nfull are whole
-    // (unrolled with compile-time block numbers: the block counter that enters the steady loop is then a function
-    // of kernel parameters alone, which is what lets ptxas keep it and the tap indices in uniform registers)
+    const int NB = R - 1 + Q;                // blocks of a thread
+    const int Qf = Lrem == D ? Q : Q - 1;    // whole tap blocks
+    const int part = Lrem == D ? 0 : Lrem;   // taps of the partial last tap block
+    const int nfull = s_end / D;             // the thread's blocks b < nfull are whole
+    // a whole tap block on one output
+    auto whole = [&](float2 &t, const float2 (&v)[D], int qb) {
+        const float *ts = taps.s + qb * D;
+        if (D % 4 == 0) {
 #pragma unroll
-    for (int bb = 0; bb < R - 1; ++bb)
-        if (bb < NB) {
-            take(bb);
-            general_block<D, R, NT, LMAX, EXACT>(X, tid, bb, s_end, Q, Lrem, taps, one, acc);
+            for (int p = 0; p < D; p += 4) {
+                const float4 f = *reinterpret_cast<const float4 *>(ts + p);
+                t = mac<EXACT>(t, v[p], make_float2(f.x, f.x), one);
+                t = mac<EXACT>(t, v[p + 1], make_float2(f.y, f.y), one);
+                t = mac<EXACT>(t, v[p + 2], make_float2(f.z, f.z), one);
+                t = mac<EXACT>(t, v[p + 3], make_float2(f.w, f.w), one);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < D; p++) t = mac<EXACT>(t, v[p], make_float2(ts[p], ts[p]), one);
         }
-    int b = min(R - 1, NB);
-    if (b + R <= Qf) {
+    };
+    // a block in which not every output has a (whole) tap block: the first R - 1 and the last few
+    auto edge_block = [&](int blk, int rb) {
+        take(blk);
         float2 v[D];
-        load_block<D, R, NT, LMAX>(X + 2 * (tid + b / R), (R - 1) % R, v); // b == R - 1 here
-        for (; b + R <= Qf; b += R) {
+        load_block<D, R, NT, LMAX>(X + 2 * (tid + blk / R), rb, v);
+        const bool on = blk < nfull;
 #pragma unroll
-            for (int k = 0; k < R; k++) {
-                float2 w[D]; // block b + k + 1 (the one after the last is inside the layout: b + R <= Qf <= NB - 1)
-                load_block<D, R, NT, LMAX>(X + 2 * (tid + (b + k + 1) / R), (R + k) % R, w);
-                const bool on = b + k < nfull;
-                take(b + k);
-                float2 t[R]; // the block's sums are kept or dropped as a whole: R selects per block, none per MAC
+        for (int r = 0; r < R; r++) {
+            const int qb = blk - r; // uniform
+            if (qb < 0 || qb >= Q) continue;
+            float2 t = acc[r];
+            if (qb < Qf) {
+                whole(t, v, qb);
+            } else {
+                const float *ts = taps.s + qb * D;
 #pragma unroll
-                for (int r = 0; r < R; r++) t[r] = acc[r];
+                for (int p = 0; p < D; p++)
+                    if (p < part) t = mac<EXACT>(t, v[p], make_float2(ts[p], ts[p]), one);
+            }
+            if (on) acc[r] = t;
+        }
+    };
+#pragma unroll
+    for (int bb = 0; bb < R - 1; ++bb) edge_block(bb, bb); // (bb < NB: every filter has at least one tap block)
+    int b = R - 1;
+    if (b < Qf) {
+        // the block's row group (b mod R) and column (b div R) are stepped, never divided
+        const float4 *xc4 = reinterpret_cast<const float4 *>(X + 2 * tid);
+        int rb = R - 1;
+        // applies block blk held in v[] to all R outputs (whole tap blocks for every output)
+        // the per-thread tests run on per-thread countdowns: comparing the block counter itself with a thread's
+        // values would pull it, and with it the tap indices, out of the uniform registers
+        int left = nfull - b; // whole blocks the thread still has
+        int until[R];         // blocks until output r's snapshot
+#pragma unroll
+        for (int r = 0; r < R; r++) until[r] = SNAP ? snap_blk[r] - b : 0;
+        auto apply = [&](const float2 (&v)[D], int blk) {
+            const bool on = left > 0;
+            left--;
+            if constexpr (SNAP) {
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    if (until[r] == 0) snap[r] = acc[r];
+                    until[r]--;
+                }
+            }
+            float2 t[R]; // the block's sums are kept or dropped as a whole: R selects per block, none per MAC
+#pragma unroll
+            for (int r = 0; r < R; r++) t[r] = acc[r];
+            if (D % 4 == 0) {
+#pragma unroll
+                for (int p = 0; p < D; p += 4) {
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const float4 f = *reinterpret_cast<const float4 *>(taps.s + (blk - r) * D + p);
+                        t[r] = mac<EXACT>(t[r], v[p], make_float2(f.x, f.x), one);
+                        t[r] = mac<EXACT>(t[r], v[p + 1], make_float2(f.y, f.y), one);
+                        t[r] = mac<EXACT>(t[r], v[p + 2], make_float2(f.z, f.z), one);
+                        t[r] = mac<EXACT>(t[r], v[p + 3], make_float2(f.w, f.w), one);
+                    }
+                }
+            } else {
 #pragma unroll
                 for (int p = 0; p < D; p++) {
 #pragma unroll
                     for (int r = 0; r < R; r++) {
-                        const float f = taps.s[(b + k - r) * D + p];
+                        const float f = taps.s[(blk - r) * D + p];
                         t[r] = mac<EXACT>(t[r], v[p], make_float2(f, f), one);
                     }
                 }
-#pragma unroll
-                for (int r = 0; r < R; r++)
-                    if (on) acc[r] = t[r];
-#pragma unroll
-                for (int p = 0; p < D; p++) v[p] = w[p];
             }
+#pragma unroll
+            for (int r = 0; r < R; r++)
+                if (on) acc[r] = t[r];
+        };
+        auto step = [&]() { // to the next block's place in the layout
+            if (++rb == R) {
+                rb = 0;
+                xc4 += 1;
+            }
+        };
+        // two blocks per iteration in two register sets: each set is loaded a whole block ahead of its use and no
+        // copy between the sets ever waits for a load (the block after the last is inside the layout: Qf <= NB - 1)
+        float2 v0[D], v1[D];
+        load_block<D, R, NT, LMAX>(reinterpret_cast<const float2 *>(xc4), rb, v0);
+        // (an explicit trip count: with `b + 2 <= Qf` as the exit test ptxas moves b to a vector register)
+        const int n2 = (Qf - (R - 1)) >> 1;
+        for (int it = 0; it < n2; ++it) {
+            const int blk = R - 1 + 2 * it; // from the trip counter alone: b itself has per-thread uses after the loop
+            step();
+            load_block<D, R, NT, LMAX>(reinterpret_cast<const float2 *>(xc4), rb, v1);
+            apply(v0, blk);
+            step();
+            load_block<D, R, NT, LMAX>(reinterpret_cast<const float2 *>(xc4), rb, v0);
+            apply(v1, blk + 1);
+        }
+        b = R - 1 + 2 * n2;
+        if ((Qf - (R - 1)) & 1) {
+            apply(v0, b);
+            ++b;
         }
     }
-    for (; b < Qf; ++b) { // up to R - 1 whole blocks left
-        float2 v[D];
-        load_block<D, R, NT, LMAX>(X + 2 * (tid + b / R), b % R, v);
-        const bool on = b < nfull;
-        take(b);
-        float2 t[R];
+    // the last blocks: b is R - 1 or Qf here, whichever is larger
 #pragma unroll
-        for (int r = 0; r < R; r++) t[r] = acc[r];
-#pragma unroll
-        for (int p = 0; p < D; p++) {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                const float f = taps.s[(b - r) * D + p];
-                t[r] = mac<EXACT>(t[r], v[p], make_float2(f, f), one);
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; r++)
-            if (on) acc[r] = t[r];
-    }
-    for (; b < NB; ++b) {
-        take(b);
-        general_block<D, R, NT, LMAX, EXACT>(X, tid, b, s_end, Q, Lrem, taps, one, acc);
-    }
-    // a truncated thread's partial last block, when it fell into the predicated range above
-    if (s_end - nfull * D > 0 && nfull >= R - 1 && nfull < Qf) general_block<D, R, NT, LMAX, EXACT>(X, tid, nfull, s_end, Q, Lrem, taps, one, acc);
+    for (int m = 0; m < R; ++m)
+        if (b + m < NB) edge_block(b + m, (b + m) % R);
+    // a truncated thread's partial last block (per-thread path: its tap count is the thread's own)
+    if (s_end - nfull * D > 0 && nfull < NB) general_block<D, R, NT, LMAX, EXACT>(X, tid, nfull, s_end, Q, Lrem, taps, one, acc);
 }
 
 // FIR + store of one tile: thread `tid` of the tile owns outputs R*tid .. R*tid+R-1; its samples sit in the
 // layout X (geometry FirGeom<D, R, NTG, LMAX>) from column xidx on
-template <int D, int R, int NTG, int LMAX, bool EXACT, int LS>
+template <int D, int R, int NTG, int LMAX, bool EXACT, int LS, bool SNAP>
 __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, const TileGeo &g, const float2 *__restrict__ X,
                                  int xidx, int tid)
 {
-    // slots [skip, cnt) of the tile are wanted; a thread takes part when any of its R slots is
-    if (static_cast<uint32_t>(R * tid) < g.cnt && static_cast<uint32_t>(R * tid + R) > g.skip) {
+    // slots [skip, cnt) of the tile are wanted; a thread takes part when any of its R slots is.  Whole WARPS enter
+    // (a vote, not a per-thread branch: the filter loops then run in warp-uniform control flow, which is what lets
+    // ptxas keep their counters and tap indices in uniform registers); a thread without slots runs them predicated
+    // off and stores nothing.
+    const bool mine = static_cast<uint32_t>(R * tid) < g.cnt && static_cast<uint32_t>(R * tid + R) > g.skip;
+    if (__any_sync(0xffffffffu, mine)) {
         const int64_t q = g.f0 + static_cast<int64_t>(R * tid); // the thread's first slot as a flat output index
         // the unit's raw buffer ends at (unit_top0 + n_call)*D + L: later samples do not exist for
         // this read (filter.rs:68-71) and the ascending tap loop stops there
@@ -896,8 +964,15 @@ __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, 
         for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f); // Complex::zero(), filter.rs:112
 
         // the tail of a read: outputs whose taps run past the end of the unit's raw buffer stop there
-        const int s_end = static_cast<int>(min(static_cast<int64_t>(s_total), s_lim));
-        if (a.tail_out) {
+        const int s_end = mine ? static_cast<int>(min(static_cast<int64_t>(s_total), s_lim)) : 0;
+        if constexpr (!SNAP) {
+            if (LS > 0) {
+                if (!__any_sync(__activemask(), s_lim < s_total)) fir_static<D, R, NTG, LMAX, EXACT, (LS > 0 ? LS : 1), false>(X, xidx, taps, one, acc, s_end);
+                else fir_static<D, R, NTG, LMAX, EXACT, (LS > 0 ? LS : 1), true>(X, xidx, taps, one, acc, s_end);
+            } else {
+                fir_dynamic<D, R, NTG, LMAX, EXACT>(X, xidx, Q, Lrem, s_end, taps, one, acc);
+            }
+        } else {
             // stream feeding overlapping windows: some outputs also leave a snapshot of their running sum
             int snap_j[R], snap_blk[R];
             uint64_t snap_at[R];
@@ -909,7 +984,7 @@ __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, 
                 snap_at[r] = 0;
                 snap[r] = make_float2(0.0f, 0.0f);
                 const int64_t qq = q + r - lead_in;
-                if (qq >= 0 && q + r < static_cast<int64_t>(a.total_out)) {
+                if (mine && qq >= 0 && q + r < static_cast<int64_t>(a.total_out)) {
                     const uint64_t u = static_cast<uint64_t>(qq) / a.tail_S;
                     const uint32_t rr = static_cast<uint32_t>(static_cast<uint64_t>(qq) - u * a.tail_S);
                     if (rr < a.tail_T && u < a.tail_units) {
@@ -920,7 +995,7 @@ __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, 
                 }
             }
             if (LS > 0) fir_static<D, R, NTG, LMAX, EXACT, (LS > 0 ? LS : 1), false, true>(X, xidx, taps, one, acc, s_end, snap_j, snap);
-            else fir_dynamic<D, R, NTG, LMAX, EXACT>(X, xidx, Q, Lrem, s_end, taps, one, acc, snap_blk, snap);
+            else fir_dynamic<D, R, NTG, LMAX, EXACT, true>(X, xidx, Q, Lrem, s_end, taps, one, acc, snap_blk, snap);
 #pragma unroll
             for (int r = 0; r < R; r++) {
                 if (snap_j[r] < 0) continue;
@@ -937,14 +1012,11 @@ __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, 
                 }
                 a.tail_out[snap_at[r]] = snap[r];
             }
-        } else if (LS > 0) {
-            if (!__any_sync(__activemask(), s_lim < s_total)) fir_static<D, R, NTG, LMAX, EXACT, (LS > 0 ? LS : 1), false>(X, xidx, taps, one, acc, s_end);
-            else fir_static<D, R, NTG, LMAX, EXACT, (LS > 0 ? LS : 1), true>(X, xidx, taps, one, acc, s_end);
-        } else {
-            fir_dynamic<D, R, NTG, LMAX, EXACT>(X, xidx, Q, Lrem, s_end, taps, one, acc);
         }
         float2 *o = a.out + q;
-        if (q >= 0 && q + R <= static_cast<int64_t>(a.total_out)) {
+        if (!mine) {
+            // no slot of this thread is wanted
+        } else if (q >= 0 && q + R <= static_cast<int64_t>(a.total_out)) {
             if (R % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
                 for (int r = 0; r < R; r += 2)
@@ -972,7 +1044,10 @@ constexpr int ctas_per_sm()
     return NT <= 128 ? 3 : 2; // long-filter shapes: a 74 KB sample layout, tiles read from global memory (no staging buffer)
 }
 
-template <int D, int R, int NT, bool EXACT, int LS>
+// SNAP: the launch also leaves snapshots of running sums (FirArgs::tail_out); a kernel of its own, so that each
+// kernel holds ONE copy of the filter loops (with two copies in one kernel ptxas keeps the tap loads of one of
+// them out of the uniform registers)
+template <int D, int R, int NT, bool EXACT, int LS, bool SNAP = false>
 __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
 {
     constexpr int LMAX = LS > 0 ? LS : kMaxTapPairs;
@@ -1090,7 +1165,7 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
             tile_phase(tile_geo<D, Gm::T_TILE>(a, tile + gridDim.x));
 
         // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
-        fir_tile<D, R, NT, LMAX, EXACT, LS>(a, taps, g, X, tid, tid);
+        fir_tile<D, R, NT, LMAX, EXACT, LS, SNAP>(a, taps, g, X, tid, tid);
         __syncthreads();
     }
 }
@@ -1101,10 +1176,16 @@ static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
     using Gm = FirGeom<D, R, NT, (LS > 0 ? LS : kMaxTapPairs)>;
     const size_t smem = kSmemHeader + Gm::X_BYTES + static_cast<size_t>(a.raw_cap) + (EXACT ? 0 : NT * sizeof(double2));
     if (smem > 227 * 1024) return set_error(QD_E_INVALID_ARG, "internal: fused FIR tile needs %zu bytes of shared memory", smem);
-    const int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
+    int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
+    if (c.fir_cta_cap > 0) per_sm = std::min(per_sm, c.fir_cta_cap);
     const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, ctas_per_sm<D, R, NT, EXACT, LS>())));
-    QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    fk_fir<D, R, NT, EXACT, LS><<<grid, NT, smem, c.stream>>>(a, t);
+    if (a.tail_out) {
+        QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        fk_fir<D, R, NT, EXACT, LS, true><<<grid, NT, smem, c.stream>>>(a, t);
+    } else {
+        QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        fk_fir<D, R, NT, EXACT, LS, false><<<grid, NT, smem, c.stream>>>(a, t);
+    }
     QD_LAUNCHED();
     return QD_OK;
 }

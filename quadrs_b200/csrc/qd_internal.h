@@ -152,6 +152,7 @@ struct Chain {
 
     // fused path (qd_fast.cu): segments are double buffered against H2D and D2H copies
     bool use_fast = true;
+    int fir_cta_cap = 0; // experiments: resident fk_fir CTAs per SM (0 = as many as fit)
     size_t segment_bytes = size_t(32) << 20; // raw bytes staged per segment for host / file sources (measured best of 16..256 MiB)
     bool pipeline_ready = false;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
