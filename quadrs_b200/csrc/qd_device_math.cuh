@@ -135,6 +135,22 @@ __device__ __forceinline__ float2 phasor_exact(uint64_t n, double ratio, const d
     return make_float2(static_cast<float>(c), static_cast<float>(s));
 }
 
+// ---- streaming global loads that do not allocate in L1: tiles read straight from global memory pass through once,
+// and must not evict the sin/cos table (8 KB, read twice per sample by the exact mixer) from the little L1 that is
+// left beside the kernel's shared memory
+__device__ __forceinline__ uint4 ldg_stream_v4(const void *p)
+{
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_stream_v2(const void *p)
+{
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
 // ---- PTX helpers: shared-window addresses, mbarriers, 1-D bulk async copies (TMA)
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 

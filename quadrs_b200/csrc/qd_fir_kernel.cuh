@@ -273,9 +273,9 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
     uint4 nlo = make_uint4(0, 0, 0, 0), nhi = make_uint4(0, 0, 0, 0);
     auto fetch = [&](uint32_t grp) {
         nlo = nhi = make_uint4(0, 0, 0, 0);
-        if (static_cast<int>(4 * grp + 1) >= n_skip) nlo = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp);
+        if (static_cast<int>(4 * grp + 1) >= n_skip) nlo = ldg_stream_v4(reinterpret_cast<const uint4 *>(raw) + 2 * grp);
         if (static_cast<int>(4 * grp + 2) < n_have && static_cast<int>(4 * grp + 3) >= n_skip)
-            nhi = __ldg(reinterpret_cast<const uint4 *>(raw) + 2 * grp + 1);
+            nhi = ldg_stream_v4(reinterpret_cast<const uint4 *>(raw) + 2 * grp + 1);
     };
     if (FMT == QD_FMT_CF32 && static_cast<uint32_t>(tid) < n_groups) fetch(tid);
     for (uint32_t grp = tid; grp < n_groups; grp += NT) {
@@ -563,15 +563,16 @@ __device__ __forceinline__ void decode_exact_global(const FirArgs &a, const uint
     double nd = __ull2double_rn(n0 + static_cast<uint64_t>(4 * idx));
     auto fetch = [&](uint32_t gc, uint32_t (&w)[4]) {
         if (FMT == QD_FMT_CS16) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(g0 + static_cast<size_t>(GB) * gc));
+            const uint4 v = ldg_stream_v4(g0 + static_cast<size_t>(GB) * gc);
             w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
         } else {
-            const uint2 v = __ldg(reinterpret_cast<const uint2 *>(g0 + static_cast<size_t>(GB) * gc));
+            const uint2 v = ldg_stream_v2(g0 + static_cast<size_t>(GB) * gc);
             w[0] = v.x, w[1] = v.y, w[2] = 0, w[3] = 0;
         }
     };
     uint32_t nxt[4] = {0, 0, 0, 0};
     if (static_cast<uint32_t>(idx) < n_loc) fetch(idx, nxt);
+#pragma unroll 2
     for (uint32_t gc = idx; gc < n_loc; gc += STRIDE, xb += STRIDE / Gm::G) {
         const uint32_t cur[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
         if (gc + STRIDE < n_loc) fetch(gc + STRIDE, nxt);
