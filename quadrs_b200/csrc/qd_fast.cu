@@ -191,7 +191,7 @@ struct TailSnap {
 
 static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const double *ratios, const uint8_t *d_src,
                       uint64_t src_base, uint64_t src_end, uint64_t off0, uint64_t n_call, uint64_t S, uint64_t n_units,
-                      uint64_t total_out, float2 *d_out, const TailSnap *snap = nullptr)
+                      uint64_t total_out, float2 *d_out, const TailSnap *snap = nullptr, const FftArgs *fuse = nullptr)
 {
     const Stage &st = *lp.st;
     FirArgs a;
@@ -235,6 +235,7 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     a.raw_cap = unstaged ? 0 : static_cast<uint32_t>(((span_max * pb + 15) / 16) * 16 + 32);
     a.out = d_out;
     a.one = make_float2(1.0f, 1.0f);
+    if (fuse) a.fft = *fuse;
     if (snap) {
         a.tail_out = snap->out;
         a.tail_W = snap->W, a.tail_S = snap->S, a.tail_T = snap->T;
@@ -306,7 +307,7 @@ static uint64_t round_up(uint64_t v, uint64_t m) { return (v + m - 1) / m * m; }
 constexpr uint64_t kStreamCall = uint64_t(1) << 40; // "one read that never ends": no truncation inside a stream
 
 // see qd_internal.h
-int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done)
+int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done, FastPrepareFn prepare)
 {
     *units_done = 0;
     const FastPlan f = fast_plan(c, unit_len, stride, n_units);
@@ -396,7 +397,20 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
         const float2 *d_top;
         uint64_t pitch;
         QD_TRY(c.prof_begin());
-        if (!f.stream_top) {
+        // sparkfft over back-to-back windows behind a run-time-length filter in EXACT arithmetic: the STFT runs inside
+        // the filter kernel (whole windows per tile, window starts on multiples of R), nothing but glyph rows is written
+        const uint64_t t_tile = static_cast<uint64_t>(top.shape.R) * top.shape.NT;
+        const bool fuse = c.fuse_stft && !f.stream_top && prepare && f.n_lp == 1 && stride == unit_len && is_pow2(unit_len) && unit_len >= 4 &&
+                          unit_len <= t_tile && top.L != 40 && c.precision == QD_PRECISION_EXACT && unit_len % top.shape.R == 0 &&
+                          soff % unit_len == 0;
+        if (fuse) {
+            FftArgs fa;
+            QD_TRY(prepare(c, user, j, u0, nu, &fa));
+            QD_TRY(launch_fir(c, top, s.format, f.n_shift, ratios, d_src, src_base, src_end, soff, unit_len, stride, nu,
+                              nu * unit_len, nullptr, nullptr, &fa));
+            d_top = nullptr;
+            pitch = unit_len;
+        } else if (!f.stream_top) {
             // [nu][unit_len] matrix straight from the raw bytes, per-unit truncation applied in the kernel
             float2 *d_out;
             if (d_direct) {
@@ -470,7 +484,7 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
                 QD_LAUNCHED();
             }
         }
-        QD_TRY(c.prof_end("fk_fir (fused decode+mix+FIR-decimate)"));
+        QD_TRY(c.prof_end(fuse ? "fk_fir (fused decode+mix+FIR-decimate+STFT+glyphs)" : "fk_fir (fused decode+mix+FIR-decimate)"));
         QD_CUDA(cudaEventRecord(c.ev_compute[j], c.stream)); // the raw staging buffer may be refilled
         if (on_segment) {
             const int rc = on_segment(c, user, j, u0, nu, d_top, pitch);

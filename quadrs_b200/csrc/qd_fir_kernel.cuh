@@ -22,6 +22,7 @@
 
 #include "qd_device_math.cuh"
 #include "qd_internal.h"
+#include "qd_stft_epilogue.cuh"
 
 namespace qd {
 
@@ -76,6 +77,10 @@ struct FirArgs {
     float2 *tail_out; // nullptr: no snapshots
     uint32_t tail_W, tail_S, tail_T;
     uint64_t tail_units;
+    // Fused sparkfft sink (fft.W != 0): the units of the launch are back-to-back windows of fft.W outputs (stride =
+    // width); a tile holds whole windows, so the kernel transforms them in shared memory right after the filter and
+    // writes glyph indices (and magnitudes) instead of the cf32 outputs -- the decimated stream never reaches HBM.
+    FftArgs fft;
 };
 
 // Per-tile phase state of the lean FAST decode, computed by one thread while the previous tile is filtered
@@ -918,9 +923,10 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
 
 // FIR + store of one tile: thread `tid` of the tile owns outputs R*tid .. R*tid+R-1; its samples sit in the
 // layout X (geometry FirGeom<D, R, NTG, LMAX>) from column xidx on
-template <int D, int R, int NTG, int LMAX, bool EXACT, int LS, bool SNAP>
-__device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, const TileGeo &g, const float2 *__restrict__ X,
-                                 int xidx, int tid)
+// FUSE: the outputs are not stored; they come back in acc[] (valid where `mine`) for the fused STFT
+template <int D, int R, int NTG, int LMAX, bool EXACT, int LS, bool SNAP, bool FUSE = false>
+__device__ __forceinline__ bool fir_tile(const FirArgs &a, const FirTaps &taps, const TileGeo &g, const float2 *__restrict__ X,
+                                 int xidx, int tid, float2 (&acc)[R])
 {
     // slots [skip, cnt) of the tile are wanted; a thread takes part when any of its R slots is.  Whole WARPS enter
     // (a vote, not a per-thread branch: the filter loops then run in warp-uniform control flow, which is what lets
@@ -960,7 +966,6 @@ __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, 
         const int Q = (L + D - 1) / D, Lrem = L - (Q - 1) * D;
         const float2 one = a.one;
 
-        float2 acc[R];
     #pragma unroll
         for (int r = 0; r < R; r++) acc[r] = make_float2(0.0f, 0.0f); // Complex::zero(), filter.rs:112
 
@@ -1015,8 +1020,8 @@ __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, 
             }
         }
         float2 *o = a.out + q;
-        if (!mine) {
-            // no slot of this thread is wanted
+        if (FUSE || !mine) {
+            // no slot of this thread is wanted, or the caller takes the outputs from acc[]
         } else if (q >= 0 && q + R <= static_cast<int64_t>(a.total_out)) {
             if (R % 2 == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
@@ -1030,6 +1035,86 @@ __device__ __forceinline__ void fir_tile(const FirArgs &a, const FirTaps &taps, 
 #pragma unroll
             for (int r = 0; r < R; r++)
                 if (q + r >= 0 && q + r < static_cast<int64_t>(a.total_out)) o[r] = acc[r];
+        }
+    }
+    return mine;
+}
+
+// ---------------------------------------------------------------------------- fused sparkfft sink
+// The tile's outputs (R per thread, in registers) are whole windows of W = a.fft.W samples.  They are laid into
+// shared memory (the sample layout X is dead once every thread has left the filter) in the leaf order of our
+// radix-4 FFT, transformed in place -- the passes, butterflies and twiddles of gk_fft, hence of the oracle, bit for
+// bit -- and leave as glyph indices / magnitudes (fft.rs:48-60).  The STFT is a few per cent of the filter's work,
+// so its passes are plain cooperative loops over the tile.
+template <int R, int NT, int T_TILE>
+__device__ __forceinline__ void fused_stft(const FirArgs &a, const TileGeo &g, float2 *__restrict__ Y, const float2 (&acc)[R],
+                                           bool mine, int tid)
+{
+    const uint32_t W = a.fft.W;
+    const int logw = 31 - __clz(W);
+    const bool odd = logw & 1;
+    const int n_r4 = logw >> 1;
+    if (mine) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t slot = static_cast<uint32_t>(R * tid + r);
+            if (slot >= g.skip && slot < g.cnt) Y[(slot & ~(W - 1)) + leaf_position(slot & (W - 1), W, n_r4, odd)] = acc[r];
+        }
+    }
+    __syncthreads();
+    if (odd) { // innermost size-2 FFTs (windows are W-aligned runs of the tile, so pairs never straddle one)
+        for (uint32_t b = tid; b < T_TILE / 2; b += NT) {
+            const float2 p = Y[2 * b], q = Y[2 * b + 1];
+            Y[2 * b] = padd(p, q);
+            Y[2 * b + 1] = psub(p, q);
+        }
+        __syncthreads();
+    }
+    int logq = odd ? 1 : 0;
+    for (uint32_t q = odd ? 2 : 1; q < W; q <<= 2, logq += 2) {
+        const uint32_t scale = W >> (logq + 2); // w(4q, j) == w(W, j * W/(4q))
+        for (uint32_t b = tid; b < T_TILE / 4; b += NT) {
+            const uint32_t wdw = b >> (logw - 2), bb = b & ((W >> 2) - 1);
+            const uint32_t blk = bb >> logq, k = bb & (q - 1);
+            float2 *base = Y + (wdw << logw) + (blk << (logq + 2)) + k;
+            float2 t0 = base[0], t1 = base[q], t2 = base[2 * q], t3 = base[3 * q];
+            if (k != 0) { // packed (re, im) arithmetic: every half is the individually rounded scalar operation
+                t1 = pmul_tw(t1, __ldg(a.fft.tw + k * scale), a.one);
+                t2 = pmul_tw(t2, __ldg(a.fft.tw + 2 * k * scale), a.one);
+                t3 = pmul_tw(t3, __ldg(a.fft.tw + 3 * k * scale), a.one);
+            }
+            pradix4(t0, t1, t2, t3);
+            base[0] = t0;
+            base[q] = t1;
+            base[2 * q] = t2;
+            base[3 * q] = t3;
+        }
+        __syncthreads();
+    }
+    // epilogue: thread t takes bins R*t .. R*t+R-1 (FFT order) of its window; their display places (bins W/2..W-1,
+    // then 0..W/2-1) are R consecutive bytes of the row when the window is at least 2R wide, so the glyphs leave as
+    // one word (index-only output through the threshold test); anything else goes bin by bin
+    static_assert(T_TILE == R * NT, "one run of R slots per thread");
+    const uint32_t i0 = static_cast<uint32_t>(R * tid);
+    if (i0 < g.skip || i0 >= g.cnt) return;
+    const uint64_t u = static_cast<uint64_t>(g.f0 + static_cast<int64_t>(i0 & ~(W - 1))) >> logw; // the window's row
+    const uint32_t pos0 = i0 & (W - 1);
+    uint8_t *row = a.fft.idx + u * W + ((pos0 + W / 2) & (W - 1));
+    if ((R == 4 || R == 8) && W >= 2 * R && !a.fft.mag && a.fft.use_thr && (reinterpret_cast<uintptr_t>(row) & 3) == 0) {
+#pragma unroll
+        for (int h = 0; h < R; h += 4) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int r = 0; r < 4; r++) word |= static_cast<uint32_t>(glyph_fast(a.fft, Y[i0 + h + r])) << (8 * r);
+            *reinterpret_cast<uint32_t *>(row + h) = word;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t i = i0 + r;
+            if (i >= g.cnt) break;
+            const uint64_t ui = static_cast<uint64_t>(g.f0 + static_cast<int64_t>(i & ~(W - 1))) >> logw;
+            emit_bin(a.fft, ui, W, i & (W - 1), Y[i]);
         }
     }
 }
@@ -1048,7 +1133,8 @@ constexpr int ctas_per_sm()
 // SNAP: the launch also leaves snapshots of running sums (FirArgs::tail_out); a kernel of its own, so that each
 // kernel holds ONE copy of the filter loops (with two copies in one kernel ptxas keeps the tap loads of one of
 // them out of the uniform registers)
-template <int D, int R, int NT, bool EXACT, int LS, bool SNAP = false>
+// FUSE: the launch's units are back-to-back sparkfft windows and the STFT runs in the same kernel (FirArgs::fft)
+template <int D, int R, int NT, bool EXACT, int LS, bool SNAP = false, bool FUSE = false>
 __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
 {
     constexpr int LMAX = LS > 0 ? LS : kMaxTapPairs;
@@ -1166,8 +1252,13 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
             tile_phase(tile_geo<D, Gm::T_TILE>(a, tile + gridDim.x));
 
         // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
-        fir_tile<D, R, NT, LMAX, EXACT, LS, SNAP>(a, taps, g, X, tid, tid);
+        float2 acc[R];
+        const bool mine = fir_tile<D, R, NT, LMAX, EXACT, LS, SNAP, FUSE>(a, taps, g, X, tid, tid, acc);
         __syncthreads();
+        if constexpr (FUSE) {
+            fused_stft<R, NT, Gm::T_TILE>(a, g, X, acc, mine, tid); // X is free: every thread has left the filter
+            __syncthreads();
+        }
     }
 }
 
@@ -1180,7 +1271,15 @@ static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
     int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
     if (c.fir_cta_cap > 0) per_sm = std::min(per_sm, c.fir_cta_cap);
     const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, ctas_per_sm<D, R, NT, EXACT, LS>())));
-    if (a.tail_out) {
+    if (a.fft.W) {
+        // instantiated for the run-time-length filter in EXACT arithmetic (the sparkfft sink needs bit-exact indices)
+        if constexpr (LS == 0 && EXACT) {
+            QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            fk_fir<D, R, NT, EXACT, LS, false, true><<<grid, NT, smem, c.stream>>>(a, t);
+        } else {
+            return set_error(QD_E_INVALID_ARG, "internal: no fused sparkfft kernel for this filter shape");
+        }
+    } else if (a.tail_out) {
         QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         fk_fir<D, R, NT, EXACT, LS, true><<<grid, NT, smem, c.stream>>>(a, t);
     } else {

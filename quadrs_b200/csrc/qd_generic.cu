@@ -14,6 +14,7 @@
 
 #include "qd_device_math.cuh"
 #include "qd_internal.h"
+#include "qd_stft_epilogue.cuh"
 
 namespace qd {
 
@@ -122,20 +123,6 @@ __global__ void gk_lowpass(GPlan p, int stage, uint32_t B, const uint32_t *__res
 }
 
 // ---- FFT of one unit per CTA in shared memory: our radix-4 DIT definition -------------------
-// Leaf position of natural index n: radix-4 digits of n, least significant first, become the most
-// significant digits of the position; a leftover top bit (odd log2 W) is the position's bit 0.
-__device__ __forceinline__ uint32_t leaf_position(uint32_t n, uint32_t W, int n_r4, bool odd)
-{
-    uint32_t p = 0, span = W;
-    for (int d = 0; d < n_r4; d++) {
-        span >>= 2;
-        p += (n & 3u) * span;
-        n >>= 2;
-    }
-    if (odd) p += n & 1u;
-    return p;
-}
-
 // A team of `team` threads transforms one window in shared memory; a CTA holds blockDim/team windows.
 __global__ void gk_fft(FftArgs a)
 {
@@ -631,6 +618,30 @@ struct FastSinkCtx {
     uint64_t raw_first = 0;
 };
 
+// STFT arguments of one fused-path segment: where its rows go (staging slot j for host sinks, the caller's device
+// buffers otherwise) and the glyph thresholds.  Also the `prepare` callback of run_units_fast.
+static int fast_sink_prepare(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, FftArgs *fa)
+{
+    FastSinkCtx *ctx = static_cast<FastSinkCtx *>(user);
+    SinkArgs &sink = *ctx->sink;
+    const size_t W = sink.width;
+    fill_fft_args(c, sink, W, fa);
+    const size_t ib = sink_idx_bytes(sink, W);
+    const bool mag = sink_has_mag(sink);
+    if (sink.space == QD_SPACE_HOST) {
+        if (ib) QD_TRY(c.ensure(c.pipe_idx[j], nu * ib));
+        if (mag) QD_TRY(c.ensure(c.pipe_mag[j], nu * W * sizeof(float)));
+        fa->idx = static_cast<uint8_t *>(c.pipe_idx[j].p);
+        fa->mag = mag ? static_cast<float *>(c.pipe_mag[j].p) : nullptr;
+    } else {
+        fa->idx = ib ? sink.idx_out + u0 * ib : nullptr;
+        fa->mag = mag ? sink.mag_out + u0 * W : nullptr;
+    }
+    fa->n_units = nu;
+    stft_finalize_args(*fa);
+    return QD_OK;
+}
+
 static int fast_segment_sink(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, const float2 *d_top, uint64_t pitch)
 {
     FastSinkCtx *ctx = static_cast<FastSinkCtx *>(user);
@@ -653,26 +664,19 @@ static int fast_segment_sink(Chain &c, void *user, int j, uint64_t u0, uint64_t 
         return QD_OK;
     }
     FftArgs fa;
-    fill_fft_args(c, sink, W, &fa);
-    fa.in = d_top;
-    fa.in_pitch = pitch; // unit_len for a [units][W] matrix, the window stride for a contiguous stream
-    fa.tail = c.seg_tail; // truncated window tails patched over the stream (run_units_fast)
-    fa.tail_len = c.seg_tail_len;
-    fa.raw = ctx->raw;
-    fa.raw_fmt = ctx->raw_fmt;
-    fa.raw_first = ctx->raw_first;
+    QD_TRY(fast_sink_prepare(c, user, j, u0, nu, &fa));
     const size_t ib = sink_idx_bytes(sink, W);
     const bool mag = sink_has_mag(sink);
-    if (to_host) {
-        if (ib) QD_TRY(c.ensure(c.pipe_idx[j], nu * ib));
-        if (mag) QD_TRY(c.ensure(c.pipe_mag[j], nu * W * sizeof(float)));
-        fa.idx = static_cast<uint8_t *>(c.pipe_idx[j].p);
-        fa.mag = mag ? static_cast<float *>(c.pipe_mag[j].p) : nullptr;
-    } else {
-        fa.idx = ib ? sink.idx_out + u0 * ib : nullptr;
-        fa.mag = mag ? sink.mag_out + u0 * W : nullptr;
+    if (d_top || ctx->raw) { // (d_top == nullptr without raw windows: the filter kernel has already run the STFT)
+        fa.in = d_top;
+        fa.in_pitch = pitch; // unit_len for a [units][W] matrix, the window stride for a contiguous stream
+        fa.tail = c.seg_tail; // truncated window tails patched over the stream (run_units_fast)
+        fa.tail_len = c.seg_tail_len;
+        fa.raw = ctx->raw;
+        fa.raw_fmt = ctx->raw_fmt;
+        fa.raw_first = ctx->raw_first;
+        QD_TRY(launch_fft(c, fa, nu));
     }
-    QD_TRY(launch_fft(c, fa, nu));
     if (to_host) {
         QD_CUDA(cudaEventRecord(c.ev_sink[j], c.stream));
         QD_CUDA(cudaStreamWaitEvent(c.d2h_stream, c.ev_sink[j], 0));
@@ -920,7 +924,9 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
                              : nullptr;
         // the fast STFT kernel can take a window's truncated tail from a patch matrix (see run_units_fast)
         c.allow_tail = fft_sink && sink.kind == SINK_SPARK && !sink.windowed && unit_len <= 4096 && is_pow2(unit_len);
-        QD_TRY(run_units_fast(c, off0, stride, n_units, unit_len, direct, fast_segment_sink, &ctx, &done));
+        // sparkfft can run inside the filter kernel (see run_units_fast)
+        const bool can_fuse = sink.kind == SINK_SPARK && !sink.windowed;
+        QD_TRY(run_units_fast(c, off0, stride, n_units, unit_len, direct, fast_segment_sink, &ctx, &done, can_fuse ? fast_sink_prepare : nullptr));
         c.allow_tail = false;
         used_pipeline = done > 0;
         produced = sink.kind == SINK_SAMPLES ? done * unit_len : done;

@@ -152,6 +152,7 @@ struct Chain {
 
     // fused path (qd_fast.cu): segments are double buffered against H2D and D2H copies
     bool use_fast = true;
+    bool fuse_stft = true; // sparkfft inside the filter kernel where the windows allow it (qd_fast.cu)
     int fir_cta_cap = 0; // experiments: resident fk_fir CTAs per SM (0 = as many as fit)
     size_t segment_bytes = size_t(32) << 20; // raw bytes staged per segment for host / file sources (measured best of 16..256 MiB)
     bool pipeline_ready = false;
@@ -225,8 +226,13 @@ int run_units(Chain &c, uint64_t off0, uint64_t stride, const uint64_t *offsets,
 // kernel has been enqueued on c.stream, with j = staging slot.
 // d_top/pitch: unit u of the segment starts at d_top + u*pitch (pitch = unit_len for a [units][n] matrix,
 // = stride when the top stage was materialised as one contiguous stream).
+struct FftArgs;
 typedef int (*FastSegmentFn)(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, const float2 *d_top, uint64_t pitch);
-int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done);
+// prepare (nullable): the sink is sparkfft and can run inside the filter kernel when the units are back-to-back
+// windows; it fills the STFT arguments (outputs of segment slot j, units u0..) and on_segment is then called with
+// d_top == nullptr: the segment's rows are already in place, only the copies to the host remain.
+typedef int (*FastPrepareFn)(Chain &c, void *user, int j, uint64_t u0, uint64_t nu, FftArgs *fa);
+int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, uint64_t unit_len, float2 *d_direct, FastSegmentFn on_segment, void *user, uint64_t *units_done, FastPrepareFn prepare = nullptr);
 
 // ---------------------------------------------------------------- STFT kernels (qd_generic.cu, qd_stft.cu)
 enum { EPI_SPARK = 0, EPI_LEVELS = 1, EPI_TAKE = 2 };
@@ -260,6 +266,7 @@ struct FftArgs {
 // graph[7] panic zone; thr[8]: smallest s with norm >= max.  false when min/max make that ill-defined.
 bool spark_thresholds(float mn, float mx, double thr[9]);
 int launch_stft_fast(Chain &c, const FftArgs &fa, uint64_t units, bool *handled);
+void stft_finalize_args(FftArgs &fa);
 
 // ---------------------------------------------------------------- single-process multi-GPU (qd_multi.cu)
 // Runs fn(i, shard i) for every shard of a sharded chain, each on its own host thread bound to the CPUs local
