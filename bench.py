@@ -540,16 +540,18 @@ def run_workload(cx, name, w, headline):
     alg_bytes = sum(p.n_samples for p in plans) * pb + n_units * out_per_unit
     prec_name = "fast" if precision == Q.FAST else "exact"
     traffic, traffic_src = None, None
-    ent = cx.traffic.get(f"{name}:{prec_name}:{samples}")
-    if ent:
-        traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
+    ent = cx.traffic.get(f"{name}:{prec_name}")
+    if ent:  # DRAM bytes of the step's kernels, from the ncu capture under profiles/, scaled to this run's samples
+        traffic, traffic_src = ent["dram_bytes_per_sample"] * samples_per_step, ent["source"]
     sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
     cob = fp32_cobound(w, precision == Q.FAST, cx.sm_count, sm_mhz)
     value = total_samples_step / (ms_dev * 1e-3) / 1e6
     achieved = alg_bytes / (ms_dev * 1e-3) / 1e9  # on the whole step's device time (every kernel of the chain)
     hbm_ceiling = peak * 1e9 / (alg_bytes / samples_per_step) / 1e6  # Msamples/s per GPU at 100 % of the measured HBM peak
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "traffic_source": traffic_src, "kernel": kern_name, "kernel_ms_per_step": kern_ms,
+            "traffic": traffic, "traffic_source": traffic_src,
+            "traffic_over_algorithmic": (traffic / alg_bytes) if traffic else None,
+            "kernel": kern_name, "kernel_ms_per_step": kern_ms,
             "kernel_frac": (alg_bytes / (kern_ms * 1e-3) / 1e9 / peak) if kern_ms > 0 else None,
             "step_ms": ms_dev, "algorithmic_bytes_per_step": alg_bytes, "peak_source": peak_src,
             "hbm_ceiling_msamples_per_s": hbm_ceiling}

@@ -179,6 +179,20 @@ static FastPlan fast_plan(const Chain &c, uint64_t unit_len, uint64_t stride, ui
     return f;
 }
 
+// FUSE = 2 scratch (values + snapshots of carry and tile, one work array per window of a tile) inside the sample
+// layout of the kernel launch_fir_dr picks for this stage: the same arithmetic as launch_fir_k
+static bool fuse_scratch_fits(const LpInfo &lp, uint64_t W, uint64_t S)
+{
+    const int D = static_cast<int>(lp.D), R = lp.shape.R, NT = lp.shape.NT;
+    const int ls = lp.L == 40 ? 40 : 0, lmax = ls ? ls : kMaxTapPairs;
+    const uint64_t t_out = static_cast<uint64_t>(R) * NT, t_tile = static_cast<uint64_t>(tile_outputs(D, R, NT, ls));
+    const uint64_t span = (t_out - 1) * D + static_cast<uint64_t>((lmax + D - 1) / D) * D + ((lmax % 4 || D % 4) ? 3 : 0);
+    const uint64_t dr = static_cast<uint64_t>(D) * R, cols = (span + dr - 1) / dr;
+    const uint64_t x_bytes = (dr / 2) * static_cast<uint64_t>(pitch_for(static_cast<int>(dr / 4), static_cast<int>(cols))) * sizeof(float4);
+    const uint64_t need = (2 * (W - 1 + t_tile) + (t_tile / S + 2) * W) * sizeof(float2);
+    return need <= x_bytes;
+}
+
 // One fused-kernel launch.  The source is raw capture bytes (fmt, shifts) or a cf32 stream from an earlier
 // stage.  n_units units of n_call outputs at unit stride S (top-level samples) starting at off0, written as
 // [n_units][n_call]; total_out limits the count in contiguous mode.
@@ -191,7 +205,8 @@ struct TailSnap {
 
 static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const double *ratios, const uint8_t *d_src,
                       uint64_t src_base, uint64_t src_end, uint64_t off0, uint64_t n_call, uint64_t S, uint64_t n_units,
-                      uint64_t total_out, float2 *d_out, const TailSnap *snap = nullptr, const FftArgs *fuse = nullptr)
+                      uint64_t total_out, float2 *d_out, const TailSnap *snap = nullptr, const FftArgs *fuse = nullptr,
+                      uint32_t fuse_stride = 0)
 {
     const Stage &st = *lp.st;
     FirArgs a;
@@ -236,6 +251,7 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     a.out = d_out;
     a.one = make_float2(1.0f, 1.0f);
     if (fuse) a.fft = *fuse;
+    a.fuse_S = fuse ? fuse_stride : 0; // != 0: overlapping windows cut from this stream launch
     if (snap) {
         a.tail_out = snap->out;
         a.tail_W = snap->W, a.tail_S = snap->S, a.tail_T = snap->T;
@@ -400,7 +416,7 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
         // sparkfft over back-to-back windows behind a run-time-length filter in EXACT arithmetic: the STFT runs inside
         // the filter kernel (whole windows per tile, window starts on multiples of R), nothing but glyph rows is written
         const uint64_t t_tile = static_cast<uint64_t>(top.shape.R) * top.shape.NT;
-        const bool fuse = c.fuse_stft && !f.stream_top && prepare && f.n_lp == 1 && stride == unit_len && is_pow2(unit_len) && unit_len >= 4 &&
+        const bool fuse = c.fuse_stft != 0 && !f.stream_top && prepare && f.n_lp == 1 && stride == unit_len && is_pow2(unit_len) && unit_len >= 4 &&
                           unit_len <= t_tile && top.L != 40 && c.precision == QD_PRECISION_EXACT && unit_len % top.shape.R == 0 &&
                           soff % unit_len == 0;
         if (fuse) {
@@ -427,11 +443,44 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
             // top-level outputs [g0, g1) as one stream; windows are cut from it at the sink's stride
             const uint64_t g0 = soff, g1 = soff + (nu - 1) * stride + unit_len;
             const uint64_t glen = round_up(g1 - g0, top.shape.R);
-            QD_TRY(c.ensure(c.pipe_out[j], glen * sizeof(float2) + 64));
-            float2 *d_out = static_cast<float2 *>(c.pipe_out[j].p);
             // Truncated tails: when every stream output belongs to at most one window's tail (stride >= T) they are
             // snapshots of the stream kernel's own running sums; otherwise fk_tail computes them on their own.
             const bool snap_tails = f.stream_tail && stride >= top.T;
+            // sparkfft inside the (top) stream kernel: windows carried from tile to tile (fk_fir FUSE = 2)
+            const uint64_t tt = tile_outputs(static_cast<int>(top.D), top.shape.R, top.shape.NT, top.L == 40 ? 40 : 0);
+            // (measured: the in-kernel transform is a plain cooperative radix-4 over shared memory, much slower per point
+            // than fk_stft's register-blocked passes; it pays only while the windows are tiny -- config 5's 4-point
+            // windows -- and costs 12 % on config 1, 37 % on config 2's 64-point windows: those stay two kernels unless
+            // the option asks for 2)
+            const bool fuse_stream = (c.fuse_stft == 2 || (c.fuse_stft == 1 && unit_len <= 16)) && prepare &&
+                                     c.precision == QD_PRECISION_EXACT && is_pow2(unit_len) && unit_len >= 4 &&
+                                     unit_len - 1 <= tt && stride >= 1 && (top.T == 0 || snap_tails) &&
+                                     fuse_scratch_fits(top, unit_len, stride);
+            if (fuse_stream) {
+                FftArgs fa;
+                QD_TRY(prepare(c, user, j, u0, nu, &fa));
+                TailSnap ts{nullptr, static_cast<uint32_t>(unit_len), static_cast<uint32_t>(stride), top.T, nu};
+                if (f.n_lp == 1) {
+                    QD_TRY(launch_fir(c, top, s.format, f.n_shift, ratios, d_src, src_base, src_end, g0, kStreamCall, kStreamCall,
+                                      1, glen, nullptr, &ts, &fa, static_cast<uint32_t>(stride)));
+                } else {
+                    const LpInfo &in = f.lp[0];
+                    const uint64_t h0 = g0 * top.D + top.i0, h1 = (g1 - 1) * top.D + top.i0 + top.L;
+                    const uint64_t hlen = round_up(h1 - h0, in.shape.R);
+                    QD_TRY(c.ensure(c.pipe_mid[j], hlen * sizeof(float2) + 64));
+                    float2 *d_mid = reinterpret_cast<float2 *>(static_cast<uint8_t *>(c.pipe_mid[j].p) + ((h0 & 1) ? 8 : 0));
+                    QD_TRY(launch_fir(c, in, s.format, f.n_shift, ratios, d_src, src_base, src_end, h0, kStreamCall, kStreamCall, 1,
+                                      hlen, d_mid));
+                    QD_TRY(launch_fir(c, top, QD_FMT_CF32, 0, nullptr, reinterpret_cast<const uint8_t *>(d_mid), h0, h1, g0,
+                                      kStreamCall, kStreamCall, 1, glen, nullptr, &ts, &fa, static_cast<uint32_t>(stride)));
+                }
+                QD_TRY(c.prof_end("fk_fir (fused decode+mix+FIR-decimate+STFT+glyphs)"));
+                QD_CUDA(cudaEventRecord(c.ev_compute[j], c.stream));
+                if (on_segment) QD_TRY(on_segment(c, user, j, u0, nu, nullptr, stride));
+                continue;
+            }
+            QD_TRY(c.ensure(c.pipe_out[j], glen * sizeof(float2) + 64));
+            float2 *d_out = static_cast<float2 *>(c.pipe_out[j].p);
             if (f.stream_tail) {
                 QD_TRY(c.ensure(c.pipe_tail[j], nu * top.T * sizeof(float2)));
                 c.seg_tail = static_cast<float2 *>(c.pipe_tail[j].p);

@@ -81,6 +81,11 @@ struct FirArgs {
     // width); a tile holds whole windows, so the kernel transforms them in shared memory right after the filter and
     // writes glyph indices (and magnitudes) instead of the cf32 outputs -- the decimated stream never reaches HBM.
     FftArgs fft;
+    // fft.W != 0 in STREAM mode (overlapping windows cut from the stream, FUSE = 2): each CTA takes a contiguous run
+    // of tiles and carries the last W - 1 outputs (and their snapshots) from tile to tile in shared memory, so every
+    // window is transformed by the tile that holds its last output.  fuse_S = the window stride in outputs.
+    uint32_t fuse_S;
+    uint32_t carry_off; // byte offset of the carry buffers inside dynamic shared memory
 };
 
 // Per-tile phase state of the lean FAST decode, computed by one thread while the previous tile is filtered
@@ -923,11 +928,13 @@ __device__ __forceinline__ void fir_dynamic(const float2 *__restrict__ X, int ti
 
 // FIR + store of one tile: thread `tid` of the tile owns outputs R*tid .. R*tid+R-1; its samples sit in the
 // layout X (geometry FirGeom<D, R, NTG, LMAX>) from column xidx on
-// FUSE: the outputs are not stored; they come back in acc[] (valid where `mine`) for the fused STFT
-template <int D, int R, int NTG, int LMAX, bool EXACT, int LS, bool SNAP, bool FUSE = false>
+// FUSE != 0: the outputs are not stored; they come back in acc[] (valid where `mine`) for the fused STFT, and with
+// FUSE == 2 the snapshots in snapv[] (bit r of snap_mask: output r has one)
+template <int D, int R, int NTG, int LMAX, bool EXACT, int LS, bool SNAP, int FUSE = 0>
 __device__ __forceinline__ bool fir_tile(const FirArgs &a, const FirTaps &taps, const TileGeo &g, const float2 *__restrict__ X,
-                                 int xidx, int tid, float2 (&acc)[R])
+                                 int xidx, int tid, float2 (&acc)[R], float2 (&snapv)[R], uint32_t &snap_mask)
 {
+    snap_mask = 0;
     // slots [skip, cnt) of the tile are wanted; a thread takes part when any of its R slots is.  Whole WARPS enter
     // (a vote, not a per-thread branch: the filter loops then run in warp-uniform control flow, which is what lets
     // ptxas keep their counters and tap indices in uniform registers); a thread without slots runs them predicated
@@ -1016,7 +1023,12 @@ __device__ __forceinline__ bool fir_tile(const FirArgs &a, const FirTaps &taps, 
                             if (p < p0) snap[r] = mac<EXACT>(snap[r], v[p], make_float2(tp[p], tp[p]), one);
                     }
                 }
-                a.tail_out[snap_at[r]] = snap[r];
+                if (FUSE == 2) {
+                    snapv[r] = snap[r];
+                    snap_mask |= 1u << r;
+                } else {
+                    a.tail_out[snap_at[r]] = snap[r];
+                }
             }
         }
         float2 *o = a.out + q;
@@ -1119,6 +1131,106 @@ __device__ __forceinline__ void fused_stft(const FirArgs &a, const TileGeo &g, f
     }
 }
 
+// The same for OVERLAPPING windows cut from a stream (stride S < width W; FUSE = 2).  A window is transformed by
+// the tile that holds its last output; the W - 1 outputs before the tile that it may also need come from the
+// carry buffers, which the CTA fills at the end of every tile (a CTA walks a contiguous run of tiles, and first
+// filters the tile before its run just to have them: `warm`).  The last T samples of a window are the snapshots of
+// the same stream outputs (FirArgs::tail_out), carried the same way.  Scratch inside the dead sample layout:
+// values and snapshots of carry + tile, then one W-point work array per window of the tile.
+template <int R, int NT, int T_TILE>
+__device__ __forceinline__ void fused_stream_stft(const FirArgs &a, const TileGeo &g, float2 *__restrict__ scratch,
+                                                  float2 *__restrict__ carry, const float2 (&acc)[R], const float2 (&snapv)[R],
+                                                  uint32_t snap_mask, bool mine, bool warm, int tid)
+{
+    const uint32_t W = a.fft.W, S = a.fuse_S, T = a.tail_T, C = W - 1;
+    const int logw = 31 - __clz(W);
+    const bool odd = logw & 1;
+    const int n_r4 = logw >> 1;
+    float2 *Yv = scratch, *Ys = scratch + (C + T_TILE), *Wk = scratch + 2 * (C + T_TILE);
+    float2 *Cv = carry, *Cs = carry + C;
+    // 1. carry + this tile's outputs and snapshots, indexed by (flat output index - f0 + C)
+    for (uint32_t i = tid; i < C; i += NT) {
+        Yv[i] = Cv[i];
+        Ys[i] = Cs[i];
+    }
+    if (mine) {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const uint32_t slot = static_cast<uint32_t>(R * tid + r);
+            if (slot >= g.skip && slot < g.cnt) {
+                Yv[C + slot] = acc[r];
+                if (snap_mask & (1u << r)) Ys[C + slot] = snapv[r];
+            }
+        }
+    }
+    __syncthreads();
+    // 2. the windows whose last output lies in this tile: u*S + W - 1 in [max(f0, 0), f0 + cnt)
+    const int64_t first_flat = g.f0 + static_cast<int64_t>(g.skip);
+    const int64_t last_flat = g.f0 + static_cast<int64_t>(g.cnt) - 1;
+    int64_t u_lo = first_flat - static_cast<int64_t>(W - 1);
+    u_lo = u_lo <= 0 ? 0 : (u_lo + S - 1) / S;
+    int64_t u_hi = last_flat - static_cast<int64_t>(W - 1); // inclusive
+    u_hi = u_hi < 0 ? -1 : u_hi / S;
+    if (u_hi >= static_cast<int64_t>(a.tail_units)) u_hi = static_cast<int64_t>(a.tail_units) - 1;
+    const uint32_t nwin = u_hi >= u_lo ? static_cast<uint32_t>(u_hi - u_lo + 1) : 0u;
+    if (!warm && nwin) {
+        // leaves
+        for (uint32_t i = tid; i < nwin * W; i += NT) {
+            const uint32_t w = i >> logw, n = i & (W - 1);
+            const int64_t y = (u_lo + w) * S + n - g.f0 + C; // index into Yv / Ys
+            Wk[(w << logw) + leaf_position(n, W, n_r4, odd)] = (n >= W - T) ? Ys[y] : Yv[y];
+        }
+        __syncthreads();
+        if (odd) {
+            for (uint32_t b = tid; b < nwin * (W / 2); b += NT) {
+                const float2 p = Wk[2 * b], q = Wk[2 * b + 1];
+                Wk[2 * b] = padd(p, q);
+                Wk[2 * b + 1] = psub(p, q);
+            }
+            __syncthreads();
+        }
+        int logq = odd ? 1 : 0;
+        for (uint32_t q = odd ? 2 : 1; q < W; q <<= 2, logq += 2) {
+            const uint32_t scale = W >> (logq + 2);
+            for (uint32_t b = tid; b < nwin * (W / 4); b += NT) {
+                const uint32_t wdw = b >> (logw - 2), bb = b & ((W >> 2) - 1);
+                const uint32_t blk = bb >> logq, k = bb & (q - 1);
+                float2 *base = Wk + (wdw << logw) + (blk << (logq + 2)) + k;
+                float2 t0 = base[0], t1 = base[q], t2 = base[2 * q], t3 = base[3 * q];
+                if (k != 0) {
+                    t1 = pmul_tw(t1, __ldg(a.fft.tw + k * scale), a.one);
+                    t2 = pmul_tw(t2, __ldg(a.fft.tw + 2 * k * scale), a.one);
+                    t3 = pmul_tw(t3, __ldg(a.fft.tw + 3 * k * scale), a.one);
+                }
+                pradix4(t0, t1, t2, t3);
+                base[0] = t0;
+                base[q] = t1;
+                base[2 * q] = t2;
+                base[3 * q] = t3;
+            }
+            __syncthreads();
+        }
+        // epilogue: four consecutive bins per step leave as one word when the output is index-only
+        const bool words = W >= 8 && !a.fft.mag && a.fft.use_thr && (reinterpret_cast<uintptr_t>(a.fft.idx) & 3) == 0;
+        if (words) {
+            for (uint32_t i = 4 * tid; i < nwin * W; i += 4 * NT) {
+                const uint32_t w = i >> logw, pos = i & (W - 1);
+                uint32_t word = 0;
+#pragma unroll
+                for (int r = 0; r < 4; r++) word |= static_cast<uint32_t>(glyph_fast(a.fft, Wk[i + r])) << (8 * r);
+                *reinterpret_cast<uint32_t *>(a.fft.idx + static_cast<uint64_t>(u_lo + w) * W + ((pos + W / 2) & (W - 1))) = word;
+            }
+        } else {
+            for (uint32_t i = tid; i < nwin * W; i += NT) emit_bin(a.fft, static_cast<uint64_t>(u_lo + (i >> logw)), W, i & (W - 1), Wk[i]);
+        }
+    }
+    // 3. the next tile's carry: the last W - 1 entries (a partial last tile has no successor)
+    for (uint32_t i = tid; i < C; i += NT) {
+        Cv[i] = Yv[T_TILE + i];
+        Cs[i] = Ys[T_TILE + i];
+    }
+}
+
 // resident CTAs per SM the kernel is compiled for (register budget) and launched at
 template <int D, int R, int NT, bool EXACT, int LS>
 constexpr int ctas_per_sm()
@@ -1134,7 +1246,7 @@ constexpr int ctas_per_sm()
 // kernel holds ONE copy of the filter loops (with two copies in one kernel ptxas keeps the tap loads of one of
 // them out of the uniform registers)
 // FUSE: the launch's units are back-to-back sparkfft windows and the STFT runs in the same kernel (FirArgs::fft)
-template <int D, int R, int NT, bool EXACT, int LS, bool SNAP = false, bool FUSE = false>
+template <int D, int R, int NT, bool EXACT, int LS, bool SNAP = false, int FUSE = 0>
 __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_fir(const __grid_constant__ FirArgs a, const __grid_constant__ FirTaps taps)
 {
     constexpr int LMAX = LS > 0 ? LS : kMaxTapPairs;
@@ -1191,10 +1303,21 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         }
     };
 
+    // Tiles of a CTA: every gridDim.x-th one -- or, when windows are carried from tile to tile (FUSE == 2), a
+    // contiguous run preceded by one warm-up tile that only fills the carry
+    uint64_t t_first = blockIdx.x, t_begin = blockIdx.x, t_last = a.n_tiles, t_step = gridDim.x;
+    if constexpr (FUSE == 2) {
+        const uint64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+        t_first = blockIdx.x * per;
+        t_last = min(t_first + per, a.n_tiles);
+        t_begin = t_first > 0 ? t_first - 1 : 0;
+        t_step = 1;
+        if (t_first >= t_last) t_begin = t_last; // no tile for this CTA
+    }
     uint64_t it = 0;
-    if (tid == 0 && blockIdx.x < a.n_tiles) issue(tile_geo<D, Gm::T_TILE>(a, blockIdx.x));
+    if (tid == 0 && t_begin < t_last) issue(tile_geo<D, Gm::T_TILE>(a, t_begin));
 
-    for (uint64_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
+    for (uint64_t tile = t_begin; tile < t_last; tile += t_step, ++it) {
         const TileGeo g = tile_geo<D, Gm::T_TILE>(a, tile);
         const uint64_t span = static_cast<uint64_t>(g.cnt - 1) * D + a.L;
         const uint32_t n_dec = static_cast<uint32_t>(min(span, a.src_end - g.n_tile0));
@@ -1246,17 +1369,22 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         }
         __syncthreads();
         // the raw bytes are consumed: fetch the next tile's while this one is filtered
-        if (tid == 0 && tile + gridDim.x < a.n_tiles) issue(tile_geo<D, Gm::T_TILE>(a, tile + gridDim.x));
+        if (tid == 0 && tile + t_step < t_last) issue(tile_geo<D, Gm::T_TILE>(a, tile + t_step));
         // the next tile's phase state: another warp's spare lane, so no warp carries both chores into the barrier
-        if (lean_mix && tid == (NT > 32 ? 32 : 0) && tile + gridDim.x < a.n_tiles)
-            tile_phase(tile_geo<D, Gm::T_TILE>(a, tile + gridDim.x));
+        if (lean_mix && tid == (NT > 32 ? 32 : 0) && tile + t_step < t_last)
+            tile_phase(tile_geo<D, Gm::T_TILE>(a, tile + t_step));
 
         // ---- FIR: thread owns outputs R*tid .. R*tid+R-1 of the tile ------------------------------
-        float2 acc[R];
-        const bool mine = fir_tile<D, R, NT, LMAX, EXACT, LS, SNAP, FUSE>(a, taps, g, X, tid, tid, acc);
+        float2 acc[R], snapv[R];
+        uint32_t snap_mask;
+        const bool mine = fir_tile<D, R, NT, LMAX, EXACT, LS, SNAP, FUSE>(a, taps, g, X, tid, tid, acc, snapv, snap_mask);
         __syncthreads();
-        if constexpr (FUSE) {
+        if constexpr (FUSE == 1) {
             fused_stft<R, NT, Gm::T_TILE>(a, g, X, acc, mine, tid); // X is free: every thread has left the filter
+            __syncthreads();
+        } else if constexpr (FUSE == 2) {
+            fused_stream_stft<R, NT, Gm::T_TILE>(a, g, X, reinterpret_cast<float2 *>(smem + a.carry_off), acc, snapv, snap_mask, mine,
+                                                 tile < t_first, tid);
             __syncthreads();
         }
     }
@@ -1266,16 +1394,33 @@ template <int D, int R, int NT, bool EXACT, int LS>
 static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
 {
     using Gm = FirGeom<D, R, NT, (LS > 0 ? LS : kMaxTapPairs)>;
-    const size_t smem = kSmemHeader + Gm::X_BYTES + static_cast<size_t>(a.raw_cap) + (EXACT ? 0 : NT * sizeof(double2));
+    size_t smem = kSmemHeader + Gm::X_BYTES + static_cast<size_t>(a.raw_cap) + (EXACT ? 0 : NT * sizeof(double2));
+    FirArgs a2 = a;
+    const bool stream_fuse = a.fft.W && a.fuse_S; // overlapping windows carried between tiles (FUSE = 2)
+    if (stream_fuse) {
+        // scratch inside the sample layout: values + snapshots of carry and tile, one work array per window
+        const size_t C = a.fft.W - 1, nwin_max = Gm::T_TILE / a.fuse_S + 2;
+        if ((2 * (C + Gm::T_TILE) + nwin_max * a.fft.W) * sizeof(float2) > Gm::X_BYTES)
+            return set_error(QD_E_INVALID_ARG, "internal: fused stream STFT scratch does not fit the sample layout");
+        a2.carry_off = static_cast<uint32_t>((smem + 15) / 16 * 16);
+        smem = a2.carry_off + 2 * C * sizeof(float2);
+    }
     if (smem > 227 * 1024) return set_error(QD_E_INVALID_ARG, "internal: fused FIR tile needs %zu bytes of shared memory", smem);
     int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));
     if (c.fir_cta_cap > 0) per_sm = std::min(per_sm, c.fir_cta_cap);
     const int grid = static_cast<int>(std::min<uint64_t>(a.n_tiles, static_cast<uint64_t>(c.ctx->sm_count) * std::min(per_sm, ctas_per_sm<D, R, NT, EXACT, LS>())));
-    if (a.fft.W) {
+    if (stream_fuse) {
+        if constexpr (EXACT) {
+            QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            fk_fir<D, R, NT, EXACT, LS, true, 2><<<grid, NT, smem, c.stream>>>(a2, t);
+        } else {
+            return set_error(QD_E_INVALID_ARG, "internal: the fused sparkfft kernels are EXACT only");
+        }
+    } else if (a.fft.W) {
         // instantiated for the run-time-length filter in EXACT arithmetic (the sparkfft sink needs bit-exact indices)
         if constexpr (LS == 0 && EXACT) {
-            QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            fk_fir<D, R, NT, EXACT, LS, false, true><<<grid, NT, smem, c.stream>>>(a, t);
+            QD_CUDA(cudaFuncSetAttribute(fk_fir<D, R, NT, EXACT, LS, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+            fk_fir<D, R, NT, EXACT, LS, false, 1><<<grid, NT, smem, c.stream>>>(a, t);
         } else {
             return set_error(QD_E_INVALID_ARG, "internal: no fused sparkfft kernel for this filter shape");
         }

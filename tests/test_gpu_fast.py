@@ -231,6 +231,8 @@ TAIL_CASES = [
     (O.CS8, [("shift", -2_000_000), ("shift", 700_000), ("lowpass", 500_000, 4, 64)], 16, 1),   # T = 7, stride 1
     (O.CS16, [("shift", 7_000_000), ("lowpass", 2_000_000, 16, 800)], 256, 255),  # T = 24, one sample of overlap
     (O.CF32, [("lowpass", 1_000_000, 8, 10)], 8, 3),                              # T = 0: plain stream
+    (O.CF32, [("lowpass", 20_000_000, 8, 40), ("lowpass", 500_000, 32, 40)], 4, 2),  # config 5: two stages, 4-point windows
+    (O.CS8, [("shift", 1_500_000), ("lowpass", 1_000_000, 8, 40)], 256, 64),      # windows half a tile wide
 ]
 
 
@@ -257,6 +259,17 @@ def test_overlapping_windows_stream_plus_tail(Q, fmt, stages, W, S):
     assert idx.shape == widx.shape and idx.shape[0] > 250
     assert np.array_equal(idx, widx) and np.array_equal(idx2, widx)
     assert_bit_equal(mag, wmag, "magnitudes")
+    # the same with the STFT never / always inside the filter kernel (fk_fir FUSE = 2: windows carried from tile to
+    # tile, snapshots for the truncated tails), in several host-path segments
+    for fuse, seg in ((0, 0), (2, 0), (2, 9_000 * O.FORMAT_BYTES[fmt])):
+        h = gpu_chain(raw, fmt, 100_000_000, stages)
+        h.set_option("fuse_stft", fuse)
+        if seg:
+            h.set_option("segment_bytes", seg)
+        fidx, fmag = h.spark_fft(W, S, rng, want_mag=True)
+        fidx2, _ = h.spark_fft(W, S, rng)
+        assert np.array_equal(fidx, widx) and np.array_equal(fidx2, widx), (fuse, seg)
+        assert_bit_equal(fmag, wmag, f"magnitudes, fuse_stft={fuse}, segment_bytes={seg}")
 
 
 # ---------------------------------------------------------------- FAST arithmetic mode
