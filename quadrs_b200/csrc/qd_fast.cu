@@ -189,7 +189,28 @@ static bool fuse_scratch_fits(const LpInfo &lp, uint64_t W, uint64_t S)
     const uint64_t span = (t_out - 1) * D + static_cast<uint64_t>((lmax + D - 1) / D) * D + ((lmax % 4 || D % 4) ? 3 : 0);
     const uint64_t dr = static_cast<uint64_t>(D) * R, cols = (span + dr - 1) / dr;
     const uint64_t x_bytes = (dr / 2) * static_cast<uint64_t>(pitch_for(static_cast<int>(dr / 4), static_cast<int>(cols))) * sizeof(float4);
-    const uint64_t need = (2 * (W - 1 + t_tile) + (t_tile / S + 2) * W) * sizeof(float2);
+    const uint64_t yn = W - 1 + t_tile + ((W - 1 + t_tile) >> 5) + 1;
+    const uint64_t need = (2 * yn + (t_tile / S + 2) * W) * sizeof(float2);
+    return need <= x_bytes;
+}
+
+// `lowpass | lowpass | sparkfft` in one kernel (FirArgs::st2_L): the outer filter's taps fit the argument block, a
+// tile completes enough outer outputs for a chunk's warm-up tile to fill the window carry, and the scratch fits
+static bool fuse_two_stage_fits(const LpInfo &in, const LpInfo &top, uint64_t W, uint64_t S)
+{
+    if (top.L > 256 || top.T != 0) return false;
+    const int D = static_cast<int>(in.D), R = in.shape.R, NT = in.shape.NT;
+    const int ls = in.L == 40 ? 40 : 0, lmax = ls ? ls : kMaxTapPairs;
+    const uint64_t t_out = static_cast<uint64_t>(R) * NT, t_tile = static_cast<uint64_t>(tile_outputs(D, R, NT, ls));
+    if (top.L - 1 > t_tile) return false;
+    // outer outputs a tile completes, less those of a warm-up tile that would need the tile before it
+    if (t_tile / top.D < (top.L - 1 + top.D - 1) / top.D + (W - 1) + 1) return false;
+    const uint64_t span = (t_out - 1) * D + static_cast<uint64_t>((lmax + D - 1) / D) * D + ((lmax % 4 || D % 4) ? 3 : 0);
+    const uint64_t dr = static_cast<uint64_t>(D) * R, cols = (span + dr - 1) / dr;
+    const uint64_t x_bytes = (dr / 2) * static_cast<uint64_t>(pitch_for(static_cast<int>(dr / 4), static_cast<int>(cols))) * sizeof(float4);
+    const uint64_t n2 = t_tile / top.D + 2;
+    const uint64_t yn = top.L - 1 + t_tile + ((top.L - 1 + t_tile) >> 5) + 1;
+    const uint64_t need = (2 * yn + (W - 1) + n2 + (n2 / S + 2) * W) * sizeof(float2);
     return need <= x_bytes;
 }
 
@@ -206,7 +227,7 @@ struct TailSnap {
 static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const double *ratios, const uint8_t *d_src,
                       uint64_t src_base, uint64_t src_end, uint64_t off0, uint64_t n_call, uint64_t S, uint64_t n_units,
                       uint64_t total_out, float2 *d_out, const TailSnap *snap = nullptr, const FftArgs *fuse = nullptr,
-                      uint32_t fuse_stride = 0)
+                      uint32_t fuse_stride = 0, const LpInfo *stage2 = nullptr, uint64_t stage2_total = 0)
 {
     const Stage &st = *lp.st;
     FirArgs a;
@@ -252,6 +273,12 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     a.one = make_float2(1.0f, 1.0f);
     if (fuse) a.fft = *fuse;
     a.fuse_S = fuse ? fuse_stride : 0; // != 0: overlapping windows cut from this stream launch
+    if (stage2) { // ... or from a second lowpass over it
+        a.st2_L = stage2->L;
+        a.st2_D = stage2->D;
+        a.st2_total = stage2_total;
+        for (uint32_t j = 0; j < stage2->L && j < 256; j++) a.st2_taps[j] = stage2->st->taps[j];
+    }
     if (snap) {
         a.tail_out = snap->out;
         a.tail_W = snap->W, a.tail_S = snap->S, a.tail_T = snap->T;
@@ -448,14 +475,17 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
             const bool snap_tails = f.stream_tail && stride >= top.T;
             // sparkfft inside the (top) stream kernel: windows carried from tile to tile (fk_fir FUSE = 2)
             const uint64_t tt = tile_outputs(static_cast<int>(top.D), top.shape.R, top.shape.NT, top.L == 40 ? 40 : 0);
-            // (measured: the in-kernel transform is a plain cooperative radix-4 over shared memory, much slower per point
-            // than fk_stft's register-blocked passes; it pays only while the windows are tiny -- config 5's 4-point
-            // windows -- and costs 12 % on config 1, 37 % on config 2's 64-point windows: those stay two kernels unless
-            // the option asks for 2)
-            const bool fuse_stream = (c.fuse_stft == 2 || (c.fuse_stft == 1 && unit_len <= 16)) && prepare &&
+            // Opt-in ("fuse_stft" = 2), because it measured SLOWER than the separate kernels on every benchmark shape:
+            // the per-tile epilogue (carry exchange, cooperative radix-4 passes over shared memory, barriers) is work
+            // the dedicated fk_stft kernel does better with register-blocked passes, and in the short-filter stream
+            // kernels -- which run at the HBM rate -- it stalls the tile loop that keeps loads in flight.  Same box,
+            // Gsamples/s: config 2's input through 64/16 windows 179 -> 111, config 1 130 -> 114, config 5 542 -> 517
+            // (STFT in the second filter's kernel) or 345 (both filters and the STFT in one kernel).
+            const bool fuse_stream = c.fuse_stft == 2 && prepare &&
                                      c.precision == QD_PRECISION_EXACT && is_pow2(unit_len) && unit_len >= 4 &&
                                      unit_len - 1 <= tt && stride >= 1 && (top.T == 0 || snap_tails) &&
-                                     fuse_scratch_fits(top, unit_len, stride);
+                                     fuse_scratch_fits(top, unit_len, stride) && glen * (f.n_lp == 2 ? top.D : 1) + top.L < (uint64_t(1) << 31) &&
+                                     nu < (uint64_t(1) << 31);
             if (fuse_stream) {
                 FftArgs fa;
                 QD_TRY(prepare(c, user, j, u0, nu, &fa));
@@ -463,6 +493,15 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
                 if (f.n_lp == 1) {
                     QD_TRY(launch_fir(c, top, s.format, f.n_shift, ratios, d_src, src_base, src_end, g0, kStreamCall, kStreamCall,
                                       1, glen, nullptr, &ts, &fa, static_cast<uint32_t>(stride)));
+                } else if (fuse_two_stage_fits(f.lp[0], top, unit_len, stride)) {
+                    // both filters and the STFT in ONE kernel: the inner stage's stream kernel carries its outputs, the
+                    // outer filter and the windows run on what each tile completes (FirArgs::st2_L)
+                    const LpInfo &in = f.lp[0];
+                    const uint64_t h0 = g0 * top.D + top.i0, h1 = (g1 - 1) * top.D + top.i0 + top.L;
+                    const uint64_t hlen = round_up(h1 - h0, in.shape.R);
+                    ts.T = 0;
+                    QD_TRY(launch_fir(c, in, s.format, f.n_shift, ratios, d_src, src_base, src_end, h0, kStreamCall, kStreamCall, 1,
+                                      hlen, nullptr, &ts, &fa, static_cast<uint32_t>(stride), &top, g1 - g0));
                 } else {
                     const LpInfo &in = f.lp[0];
                     const uint64_t h0 = g0 * top.D + top.i0, h1 = (g1 - 1) * top.D + top.i0 + top.L;

@@ -86,6 +86,13 @@ struct FirArgs {
     // window is transformed by the tile that holds its last output.  fuse_S = the window stride in outputs.
     uint32_t fuse_S;
     uint32_t carry_off; // byte offset of the carry buffers inside dynamic shared memory
+    // A SECOND lowpass between this launch's stream and the windows (st2_L != 0; config 5's `lowpass | lowpass |
+    // sparkfft`): its output k (st2_L taps at decimation st2_D over this launch's outputs, none of them truncated)
+    // is computed by the tile that holds its last input, from the carried outputs, and the windows are cut from
+    // those second-stage outputs.  Neither intermediate stream reaches HBM.
+    uint32_t st2_L, st2_D;
+    uint64_t st2_total; // second-stage outputs the windows need
+    float st2_taps[256];
 };
 
 // Per-tile phase state of the lean FAST decode, computed by one thread while the previous tile is filtered
@@ -997,7 +1004,7 @@ __device__ __forceinline__ bool fir_tile(const FirArgs &a, const FirTaps &taps, 
                 snap_at[r] = 0;
                 snap[r] = make_float2(0.0f, 0.0f);
                 const int64_t qq = q + r - lead_in;
-                if (mine && qq >= 0 && q + r < static_cast<int64_t>(a.total_out)) {
+                if (a.tail_T != 0 && mine && qq >= 0 && q + r < static_cast<int64_t>(a.total_out)) {
                     const uint64_t u = static_cast<uint64_t>(qq) / a.tail_S;
                     const uint32_t rr = static_cast<uint32_t>(static_cast<uint64_t>(qq) - u * a.tail_S);
                     if (rr < a.tail_T && u < a.tail_units) {
@@ -1142,43 +1149,85 @@ __device__ __forceinline__ void fused_stream_stft(const FirArgs &a, const TileGe
                                                   float2 *__restrict__ carry, const float2 (&acc)[R], const float2 (&snapv)[R],
                                                   uint32_t snap_mask, bool mine, bool warm, int tid)
 {
-    const uint32_t W = a.fft.W, S = a.fuse_S, T = a.tail_T, C = W - 1;
+    const uint32_t W = a.fft.W, S = a.fuse_S, T = a.tail_T, L2 = a.st2_L, D2 = a.st2_D;
+    const uint32_t C1 = L2 ? L2 - 1 : W - 1; // carried outputs of this launch's stream
+    const uint32_t C2 = L2 ? W - 1 : 0;      // carried second-stage outputs
+    const uint32_t N2 = L2 ? T_TILE / D2 + 2 : 0;
     const int logw = 31 - __clz(W);
     const bool odd = logw & 1;
     const int n_r4 = logw >> 1;
-    float2 *Yv = scratch, *Ys = scratch + (C + T_TILE), *Wk = scratch + 2 * (C + T_TILE);
-    float2 *Cv = carry, *Cs = carry + C;
-    // 1. carry + this tile's outputs and snapshots, indexed by (flat output index - f0 + C)
-    for (uint32_t i = tid; i < C; i += NT) {
-        Yv[i] = Cv[i];
-        Ys[i] = Cs[i];
+    // (stream outputs sit at ysk(index): one slot of skew per 32, so that the second stage's threads, D2 outputs
+    // apart, do not all read one bank)
+    auto ysk = [](uint32_t y) { return y + (y >> 5); };
+    const uint32_t YN = ysk(C1 + T_TILE) + 1;
+    float2 *Yv = scratch, *Ys = Yv + YN, *Zv = Ys + YN, *Wk = Zv + (C2 + N2);
+    float2 *Cv = carry, *Cs = Cv + C1, *Cz = Cs + C1;
+    // 1. carry + this tile's outputs and snapshots, indexed by (flat output index - f0 + C1)
+    for (uint32_t i = tid; i < C1; i += NT) {
+        Yv[ysk(i)] = Cv[i];
+        Ys[ysk(i)] = Cs[i];
     }
+    for (uint32_t i = tid; i < C2; i += NT) Zv[i] = Cz[i];
     if (mine) {
 #pragma unroll
         for (int r = 0; r < R; r++) {
             const uint32_t slot = static_cast<uint32_t>(R * tid + r);
             if (slot >= g.skip && slot < g.cnt) {
-                Yv[C + slot] = acc[r];
-                if (snap_mask & (1u << r)) Ys[C + slot] = snapv[r];
+                Yv[ysk(C1 + slot)] = acc[r];
+                if (snap_mask & (1u << r)) Ys[ysk(C1 + slot)] = snapv[r];
             }
         }
     }
     __syncthreads();
-    // 2. the windows whose last output lies in this tile: u*S + W - 1 in [max(f0, 0), f0 + cnt)
-    const int64_t first_flat = g.f0 + static_cast<int64_t>(g.skip);
-    const int64_t last_flat = g.f0 + static_cast<int64_t>(g.cnt) - 1;
-    int64_t u_lo = first_flat - static_cast<int64_t>(W - 1);
-    u_lo = u_lo <= 0 ? 0 : (u_lo + S - 1) / S;
-    int64_t u_hi = last_flat - static_cast<int64_t>(W - 1); // inclusive
-    u_hi = u_hi < 0 ? -1 : u_hi / S;
-    if (u_hi >= static_cast<int64_t>(a.tail_units)) u_hi = static_cast<int64_t>(a.tail_units) - 1;
+    // (32-bit index arithmetic: the host fuses only launches of fewer than 2^31 stream outputs)
+    const int f0 = static_cast<int>(g.f0);
+    const int first_flat = f0 + static_cast<int>(g.skip); // stream outputs this tile adds
+    const int last_flat = f0 + static_cast<int>(g.cnt) - 1;
+    // what the windows are cut from: this stream (with snapshots for their truncated tails) or the second stage
+    const bool from_y = L2 == 0;
+    int src_base = f0 - static_cast<int>(C1);   // flat index of element 0 of the source
+    int new_lo = first_flat, new_hi = last_flat; // flat range of the source elements this tile adds
+    uint32_t n2 = 0;
+    if (L2) {
+        // second-stage outputs whose last input is one of this tile's outputs: k*D2 + L2 - 1 in [first_flat, last_flat]
+        int k_lo = first_flat - static_cast<int>(L2 - 1);
+        k_lo = k_lo <= 0 ? 0 : (k_lo + static_cast<int>(D2) - 1) / static_cast<int>(D2);
+        int k_hi = last_flat - static_cast<int>(L2 - 1);
+        k_hi = k_hi < 0 ? -1 : k_hi / static_cast<int>(D2);
+        if (k_hi >= static_cast<int>(a.st2_total)) k_hi = static_cast<int>(a.st2_total) - 1;
+        n2 = k_hi >= k_lo ? static_cast<uint32_t>(k_hi - k_lo + 1) : 0u;
+        for (uint32_t i = tid; i < n2; i += NT) {
+            const uint32_t y0 = static_cast<uint32_t>((k_lo + static_cast<int>(i)) * static_cast<int>(D2) - f0 + static_cast<int>(C1));
+            float2 z = make_float2(0.0f, 0.0f); // ascending taps, product and sum rounded separately (filter.rs:112-120)
+            uint32_t j = 0;
+            for (; j + 8 <= L2; j += 8) { // eight loads in flight; the sum itself stays one chain in tap order
+                float2 v[8];
+                float t[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[e] = Yv[ysk(y0 + j + e)], t[e] = a.st2_taps[j + e];
+#pragma unroll
+                for (int e = 0; e < 8; e++) z = fma2(mul2(v[e], make_float2(t[e], t[e])), a.one, z);
+            }
+            for (; j < L2; j++) z = fma2(mul2(Yv[ysk(y0 + j)], make_float2(a.st2_taps[j], a.st2_taps[j])), a.one, z);
+            Zv[C2 + i] = z;
+        }
+        __syncthreads();
+        src_base = k_lo - static_cast<int>(C2);
+        new_lo = k_lo, new_hi = k_hi;
+    }
+    // 2. the windows whose last element is one the tile added: u*S + W - 1 in [new_lo, new_hi]
+    int u_lo = new_lo - static_cast<int>(W - 1);
+    u_lo = u_lo <= 0 ? 0 : (u_lo + static_cast<int>(S) - 1) / static_cast<int>(S);
+    int u_hi = new_hi - static_cast<int>(W - 1); // inclusive
+    u_hi = u_hi < 0 ? -1 : u_hi / static_cast<int>(S);
+    if (u_hi >= static_cast<int>(a.tail_units)) u_hi = static_cast<int>(a.tail_units) - 1;
     const uint32_t nwin = u_hi >= u_lo ? static_cast<uint32_t>(u_hi - u_lo + 1) : 0u;
     if (!warm && nwin) {
         // leaves
         for (uint32_t i = tid; i < nwin * W; i += NT) {
             const uint32_t w = i >> logw, n = i & (W - 1);
-            const int64_t y = (u_lo + w) * S + n - g.f0 + C; // index into Yv / Ys
-            Wk[(w << logw) + leaf_position(n, W, n_r4, odd)] = (n >= W - T) ? Ys[y] : Yv[y];
+            const uint32_t y = static_cast<uint32_t>((u_lo + static_cast<int>(w)) * static_cast<int>(S) + static_cast<int>(n) - src_base);
+            Wk[(w << logw) + leaf_position(n, W, n_r4, odd)] = from_y ? ((n >= W - T) ? Ys[ysk(y)] : Yv[ysk(y)]) : Zv[y];
         }
         __syncthreads();
         if (odd) {
@@ -1224,11 +1273,13 @@ __device__ __forceinline__ void fused_stream_stft(const FirArgs &a, const TileGe
             for (uint32_t i = tid; i < nwin * W; i += NT) emit_bin(a.fft, static_cast<uint64_t>(u_lo + (i >> logw)), W, i & (W - 1), Wk[i]);
         }
     }
-    // 3. the next tile's carry: the last W - 1 entries (a partial last tile has no successor)
-    for (uint32_t i = tid; i < C; i += NT) {
-        Cv[i] = Yv[T_TILE + i];
-        Cs[i] = Ys[T_TILE + i];
+    // 3. the next tile's carries: the last C1 stream outputs (a partial last tile has no successor) and the last C2
+    // second-stage outputs
+    for (uint32_t i = tid; i < C1; i += NT) {
+        Cv[i] = Yv[ysk(T_TILE + i)];
+        Cs[i] = Ys[ysk(T_TILE + i)];
     }
+    for (uint32_t i = tid; i < C2; i += NT) Cz[i] = Zv[n2 + i];
 }
 
 // resident CTAs per SM the kernel is compiled for (register budget) and launched at
@@ -1399,11 +1450,15 @@ static int launch_fir_k(Chain &c, const FirArgs &a, const FirTaps &t)
     const bool stream_fuse = a.fft.W && a.fuse_S; // overlapping windows carried between tiles (FUSE = 2)
     if (stream_fuse) {
         // scratch inside the sample layout: values + snapshots of carry and tile, one work array per window
-        const size_t C = a.fft.W - 1, nwin_max = Gm::T_TILE / a.fuse_S + 2;
-        if ((2 * (C + Gm::T_TILE) + nwin_max * a.fft.W) * sizeof(float2) > Gm::X_BYTES)
+        const size_t C1 = a.st2_L ? a.st2_L - 1 : a.fft.W - 1, C2 = a.st2_L ? a.fft.W - 1 : 0;
+        const size_t n2 = a.st2_L ? Gm::T_TILE / a.st2_D + 2 : 0;
+        const size_t nwin_max = (a.st2_L ? n2 : Gm::T_TILE) / a.fuse_S + 2;
+        const size_t yn = C1 + Gm::T_TILE + ((C1 + Gm::T_TILE) >> 5) + 1; // skewed (fused_stream_stft ysk)
+        if (a.total_out >= (uint64_t(1) << 31) || a.tail_units >= (uint64_t(1) << 31) ||
+            (2 * yn + C2 + n2 + nwin_max * a.fft.W) * sizeof(float2) > Gm::X_BYTES)
             return set_error(QD_E_INVALID_ARG, "internal: fused stream STFT scratch does not fit the sample layout");
         a2.carry_off = static_cast<uint32_t>((smem + 15) / 16 * 16);
-        smem = a2.carry_off + 2 * C * sizeof(float2);
+        smem = a2.carry_off + (2 * C1 + C2) * sizeof(float2);
     }
     if (smem > 227 * 1024) return set_error(QD_E_INVALID_ARG, "internal: fused FIR tile needs %zu bytes of shared memory", smem);
     int per_sm = std::max<int>(1, static_cast<int>((227 * 1024) / (smem + 1024)));

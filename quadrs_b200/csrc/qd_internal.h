@@ -152,8 +152,8 @@ struct Chain {
 
     // fused path (qd_fast.cu): segments are double buffered against H2D and D2H copies
     bool use_fast = true;
-    int fuse_stft = 1; // sparkfft inside the filter kernel: 0 never, 1 where it pays (back-to-back windows; overlapping
-                       // windows of at most 16 points), 2 wherever the kernels allow it (qd_fast.cu)
+    int fuse_stft = 1; // sparkfft inside the filter kernel: 0 never, 1 for back-to-back windows (stride = width), 2 also for
+                       // overlapping windows and two-stage chains (measured slower than the separate kernels: qd_fast.cu)
     int fir_cta_cap = 0; // experiments: resident fk_fir CTAs per SM (0 = as many as fit)
     size_t segment_bytes = size_t(32) << 20; // raw bytes staged per segment for host / file sources (measured best of 16..256 MiB)
     bool pipeline_ready = false;
