@@ -54,6 +54,10 @@ extern "C" {
     pub fn qd_last_error() -> *const c_char;
     pub fn qd_chain_create(src: *const qd_source, stages: *const qd_stage, n_stages: usize, device: c_int,
                            out: *mut *mut qd_chain) -> c_int;
+    /// One process, several GPUs: every sink call fans out over `devices` and gathers into the caller's one buffer.
+    pub fn qd_chain_create_sharded(src: *const qd_source, stages: *const qd_stage, n_stages: usize,
+                                   devices: *const c_int, n_dev: usize, out: *mut *mut qd_chain) -> c_int;
+    pub fn qd_chain_n_devices(c: *const qd_chain, n_dev: *mut usize) -> c_int;
     pub fn qd_chain_destroy(c: *mut qd_chain);
     pub fn qd_chain_len(c: *const qd_chain, len: *mut u64) -> c_int;
     pub fn qd_chain_sample_rate(c: *const qd_chain, rate: *mut u64) -> c_int;

@@ -16,7 +16,7 @@ for item in cfg4:268435456:exact cfg1:67108864:exact cfg2:268435456:fast cfg2:26
   python bench.py $A > $O/${TAG}_plain_${wl}_$P.log 2>&1 &&
   ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $O/${TAG}_launches_${wl}_$P.csv python bench.py $A > /dev/null 2>&1
   # the third warm-up step onwards: one step's worth of our kernels
-  K=3; [ $wl = cfg4 ] && K=2; [ $wl = cfg3 ] && K=1; [ $wl = cfg2 ] && K=1; [ $wl = cfg5 ] && K=3
+  K=2; [ $wl = cfg4 ] && K=1; [ $wl = cfg3 ] && K=1; [ $wl = cfg2 ] && K=1; [ $wl = cfg5 ] && K=3
   SK=$((2*K)); [ $wl = cfg5 ] && SK=24
   python bench.py $A > /dev/null 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:'fk_fir|fk_tail|fk_stft' -s $SK -c $K -f -o $O/${TAG}_full_${wl}_$P python bench.py $A > $O/${TAG}_ncuf_${wl}_$P.log 2>&1
