@@ -110,3 +110,22 @@ def test_shard_plan_covers_units_once_with_halo(Q, cfg, n_shards):
     if n_shards > 1 and plans[0].n_units and plans[1].n_units:
         overlap = plans[0].first_sample + plans[0].n_samples - plans[1].first_sample
         assert overlap == need - step * mult
+
+
+def test_sharded_chain_argument_checks_need_no_device(Q):
+    """qd_chain_create_sharded validates its arguments before it touches CUDA (include/quadrs_gpu.h)."""
+    import ctypes as C
+    L = Q._lib
+    lib = L.lib()
+    src = L.Source()
+    src.kind, src.format, src.sample_rate = L.SRC_HOST_MEM, L.FMT_CS8, 1000
+    buf = np.zeros(64, dtype=np.uint8)
+    src.data, src.n_bytes = buf.ctypes.data, buf.size
+    h = C.c_void_p()
+    devs = (C.c_int * 2)(0, 1)
+    assert lib.qd_chain_create_sharded(C.byref(src), None, 0, None, 2, C.byref(h)) == L.E_INVALID_ARG
+    assert lib.qd_chain_create_sharded(C.byref(src), None, 0, devs, 0, C.byref(h)) == L.E_INVALID_ARG
+    src.kind = L.SRC_DEVICE_MEM  # a device-resident capture lives on one device
+    assert lib.qd_chain_create_sharded(C.byref(src), None, 0, devs, 2, C.byref(h)) == L.E_INVALID_ARG
+    assert b"one device" in lib.qd_last_error()
+    assert h.value is None
