@@ -248,10 +248,11 @@ __device__ __forceinline__ float2 cmul_fast(float2 a, float2 b)
     return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
 }
 
+template <bool HALF>
 __device__ __forceinline__ float2 mix_exact(float2 v, double nd, double ratio, const FirArgs &a)
 {
     double c, sn;
-    sincos_f64k(__dmul_rn(nd, ratio), a.sincos, a.k, c, sn); // place = (off + i) as f64 * ratio, shift.rs:49
+    sincos_f64k<HALF>(__dmul_rn(nd, ratio), a.sincos, a.k, c, sn); // place = (off + i) as f64 * ratio, shift.rs:49
     return cmul_exact(v, make_float2(static_cast<float>(c), static_cast<float>(sn)));
 }
 
@@ -342,8 +343,8 @@ __device__ __forceinline__ void decode_tile(const FirArgs &a, const uint8_t *raw
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const double nd = __dadd_rn(nd0, static_cast<double>(i));
-                v[i] = mix_exact(v[i], nd, a.ratio[0], a);
-                for (int s = 1; s < n_shift; s++) v[i] = mix_exact(v[i], nd, a.ratio[s], a);
+                v[i] = mix_exact<(D <= 8)>(v[i], nd, a.ratio[0], a);
+                for (int s = 1; s < n_shift; s++) v[i] = mix_exact<(D <= 8)>(v[i], nd, a.ratio[s], a);
             }
         }
         float4 *X4 = reinterpret_cast<float4 *>(X);
@@ -553,7 +554,7 @@ __device__ __forceinline__ void mix_group_exact(const FirArgs &a, float2 (&x)[4]
     const float2 one = a.one;
     auto mix = [&](float2 v, double ni, double ratio) {
         double c, sn;
-        sincos_f64k(__dmul_rn(ni, ratio), a.sincos, a.k, c, sn);
+        sincos_f64k<false>(__dmul_rn(ni, ratio), a.sincos, a.k, c, sn); // (long-filter kernels: the full table)
         const float cf = static_cast<float>(c), sf = static_cast<float>(sn);
         const float2 p1 = mul2(make_float2(v.x, v.x), make_float2(cf, sf));
         const float2 p2 = mul2(make_float2(v.y, v.y), make_float2(-sf, cf));

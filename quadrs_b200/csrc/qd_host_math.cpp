@@ -72,18 +72,19 @@ void sincos_table(double *out)
 {
     // cos/sin(2 pi i / 256) as double-double, from 80-bit long double evaluation.
     const long double tau = 6.283185307179586476925286766559005768L;
-    for (int i = 0; i < 256; i++) {
+    // The second half turn is the exact negation of the first (e^{i(x + pi)} = -e^{ix}): the device reads only
+    // entries 0..127 and flips signs (sincos_f64k), the rest is kept for inspection.
+    for (int i = 0; i < 128; i++) {
         const long double a = tau * static_cast<long double>(i) / 256.0L;
         long double c = cosl(a), s = sinl(a);
         if (i == 0) { c = 1.0L; s = 0.0L; }
         if (i == 64) { c = 0.0L; s = 1.0L; }
-        if (i == 128) { c = -1.0L; s = 0.0L; }
-        if (i == 192) { c = 0.0L; s = -1.0L; }
         const double ch = static_cast<double>(c), sh = static_cast<double>(s);
         out[4 * i + 0] = ch;
         out[4 * i + 1] = static_cast<double>(c - static_cast<long double>(ch));
         out[4 * i + 2] = sh;
         out[4 * i + 3] = static_cast<double>(s - static_cast<long double>(sh));
+        for (int j = 0; j < 4; j++) out[4 * (i + 128) + j] = -out[4 * i + j];
     }
 }
 
