@@ -118,8 +118,11 @@ __device__ __forceinline__ void sincos_f64k(double theta, const double *__restri
     // is worth more than the four sign flips cost: config 2 EXACT 257 -> 324 Gsamples/s with 128 entries (327 with 64).
     const int kf = __double2loint(t);
     const int ki = kf & (HALF ? 127 : 255);
-    const double2 *tp = reinterpret_cast<const double2 *>(tab) + 2 * ki;
-    double2 tcos = __ldg(tp), tsin = __ldg(tp + 1); // {ch, cl}, {sh, sl}
+    // one 256-bit load per entry {ch, cl, sh, sl} (LDG.E.256, sm_100): half the L1 lookups of two 128-bit loads
+    double2 tcos, tsin;
+    asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];"
+        : "=d"(tcos.x), "=d"(tcos.y), "=d"(tsin.x), "=d"(tsin.y)
+        : "l"(tab + 4 * ki));
     if (HALF) {
         const int neg = (kf & 128) << 24; // sign-bit mask
         tcos.x = __hiloint2double(__double2hiint(tcos.x) ^ neg, __double2loint(tcos.x));
