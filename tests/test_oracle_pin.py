@@ -84,6 +84,35 @@ def test_config1_fsk_structure(golden_dir):
     assert (left ^ right).mean() > 0.8
 
 
+def test_config1_against_the_readme_screenshot(golden_dir):
+    """screenshots/fsk-5.png (README.md:90-94) is a bilevel image of the reference's own terminal output for config 1:
+    45 text rows of 19 px, 64 glyph cells of 10 px (first cell at x = 3), a white bar where the glyph is not blank.
+    The picture is periodic (the FSK alternates every ~5 rows), so the row offset is found by best agreement; at it
+    99.5 % of the 2880 cells agree with the oracle (2865), and every difference is a single cell at the edge of one of
+    the two FSK columns -- magnitudes next to the 0.08 threshold -- so this pins the pipeline's structure and scale
+    (which bins, which rows, the threshold) against a run of the real reference, not bit-exactness."""
+    Image = pytest.importorskip("PIL.Image")
+    a = np.array(Image.open(golden_dir / "readme-fsk-5.png").convert("L")) > 127
+    assert a.shape == (854, 640)
+    shot = np.zeros((45, 64), dtype=bool)
+    for r in range(45):
+        band = a[12 + 19 * r - 8: 12 + 19 * r + 6]
+        for c in range(63):
+            shot[r, c] = band[:, 3 + 10 * c: 13 + 10 * c].any()
+    assert set(np.nonzero(shot.any(axis=0))[0].tolist()) == {24, 25, 47, 48}
+    c = O.Samples.from_file(golden_dir / "fsk-example.sr21M.fc32", O.CF32, 21_000_000).shift(280_000).lowpass(200_000, 32, 400)
+    O.set_kept_only(True)
+    try:
+        idx, _ = c.spark_fft(64, 16)
+    finally:
+        O.set_kept_only(False)
+    agree = np.array([((idx[r0:r0 + 45] > 0) == shot).sum() for r0 in range(idx.shape[0] - 44)])
+    assert agree.max() >= 0.99 * shot.size, agree.max()
+    r0 = int(agree.argmax())
+    bad = np.argwhere((idx[r0:r0 + 45] > 0) != shot)
+    assert all(int(col) in (24, 25, 47, 48) for _, col in bad)  # only the edges of the two FSK columns differ
+
+
 def test_oracle_reproduces_committed_golden_vectors(golden_dir):
     # tests/golden/*.npy were produced by tests/golden/make_golden.py with the literal convolve
     s = O.Samples.from_file(golden_dir / "cupboard-superdec.sr400.cf32", O.CF32, 400)
