@@ -577,7 +577,7 @@ def run_workload(cx, name, w, headline):
     return res
 
 
-def run_e2e(cx, name, w, plans, total, precision, build_chain, d_in, d_out, out_per_unit, n_units_rank):
+def _run_e2e_rank0(cx, name, w, plans, total, precision, build_chain, d_in, d_out, out_per_unit, n_units_rank):
     """Pinned host capture -> H2D -> kernels -> D2H of the result, inside the timed region, through the C ABI.  With
     several GPUs rank 0 alone drives all of them with one sharded chain (the other ranks wait at a CPU barrier)."""
     import torch
@@ -590,7 +590,7 @@ def run_e2e(cx, name, w, plans, total, precision, build_chain, d_in, d_out, out_
     sk = sink_kind(w)
     mult, _ = chain_geometry(w)
     res = None
-    if rank == 0:
+    if True:
         if world == 1:
             # the capture of every pass is this rank's resident range
             n_host = max(p.n_samples for p in plans)
@@ -651,7 +651,20 @@ def run_e2e(cx, name, w, plans, total, precision, build_chain, d_in, d_out, out_
                "driver": "one host process" + (f", one sharded chain over {world} devices (qd_chain_create_sharded)"
                                                 if devices else "")}
         del chains
-    cx.cpu_barrier()
+    return res
+
+
+def run_e2e(cx, name, w, plans, total, precision, build_chain, d_in, d_out, out_per_unit, n_units_rank):
+    """Rank 0 measures; every rank meets at the CPU barrier afterwards, whatever happened (a failed pinned
+    allocation on a small host must not cost the headline or hang the other ranks)."""
+    res = None
+    try:
+        if cx.rank == 0:
+            res = _run_e2e_rank0(cx, name, w, plans, total, precision, build_chain, d_in, d_out, out_per_unit, n_units_rank)
+    except Exception as e:  # noqa: BLE001
+        res = {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        cx.cpu_barrier()
     return res
 
 
@@ -663,6 +676,17 @@ def host_copy_peak(cx):
     if cx.rank != 0:
         cx.cpu_barrier()
         return None
+    try:
+        return _host_copy_peak_rank0(cx)
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
+    finally:
+        cx.cpu_barrier()
+
+
+def _host_copy_peak_rank0(cx):
+    import torch
+
     n = 1 << 30
     h = cx.pinned_in(n * cx.world)
     bufs, streams = [], []
@@ -684,7 +708,6 @@ def host_copy_peak(cx):
         once()
     dt = (time.perf_counter() - t0) / 3
     del bufs
-    cx.cpu_barrier()
     return {"h2d_gb_per_s": cx.world * n / dt / 1e9, "devices": cx.world,
             "how": "1 GiB per device from one pinned buffer, all devices at once, 3 repeats, wall clock"}
 
@@ -776,7 +799,7 @@ def run_b200(args):
                 line[k] = head[k]
         if copy_peak:
             line["host_copy_peak"] = copy_peak
-            if "e2e" in line:
+            if "e2e" in line and "ms_per_step" in line["e2e"] and "h2d_gb_per_s" in copy_peak:
                 bps = line["e2e"]["h2d_bytes_per_step"] / (line["e2e"]["ms_per_step"] * 1e-3) / 1e9
                 line["e2e"]["h2d_gb_per_s"] = bps
                 line["e2e"]["frac_of_host_copy_peak"] = bps / copy_peak["h2d_gb_per_s"]

@@ -26,6 +26,9 @@
 
 namespace qd {
 
+#ifndef QD_EXP_EXACT_CTAS
+#define QD_EXP_EXACT_CTAS 5
+#endif
 constexpr int kMaxTapPairs = 1024;
 constexpr int kMaxLeadShifts = 4;
 
@@ -1288,7 +1291,7 @@ template <int D, int R, int NT, bool EXACT, int LS>
 constexpr int ctas_per_sm()
 {
     if (NT <= 128 && D <= 8) {
-        if (LS > 0) return (R <= 2 ? 8 : 5) * (128 / NT);
+        if (LS > 0) return (R <= 2 ? 8 : (EXACT ? QD_EXP_EXACT_CTAS : 5)) * (128 / NT);
         return 4 * (128 / NT);
     }
     return NT <= 128 ? 3 : 2; // long-filter shapes: a 74 KB sample layout, tiles read from global memory (no staging buffer)

@@ -111,3 +111,27 @@ def test_config1_pipeline_and_write_roundtrip(cli, golden_dir, tmp_path):
     assert np.array_equal(data.view(np.uint32), want.view(np.uint32))
     r = run(cli, "gen", "-cos", "1000", "-len", "0.01", "48k", "bucket", "-width", "64", "-by", "freq", "2")
     assert r.returncode == 0 and set(r.stdout.strip()) <= {"0", "1"} and len(r.stdout.strip()) == (480 - 64) // 64
+
+
+@pytest.mark.gpu
+def test_gpus_option_shards_one_process_over_the_devices(cli, golden_dir, tmp_path):
+    """`quadrs_gpu --gpus N ...`: the same command line on N devices of the box (qd_chain_create_sharded): stdout and
+    the written file are byte-identical to the one-device run."""
+    import numpy as np
+    import torch
+
+    n = min(torch.cuda.device_count(), 8)
+    if n < 2:
+        pytest.skip("one GPU visible")
+    fixture = golden_dir / "fsk-example.sr21M.fc32"
+    cmd = ["from", str(fixture), "shift", "280000", "lowpass", "-power", "200", "-decimate", "32", "200000"]
+    one = run(cli, *cmd, "sparkfft", "-width", "64", "-stride", "16")
+    many = run(cli, "--gpus", str(n), *cmd, "sparkfft", "-width", "64", "-stride", "16")
+    assert one.returncode == 0 and many.returncode == 0, many.stderr
+    assert many.stdout == one.stdout
+    r1 = run(cli, *cmd, "write", str(tmp_path / "a"))
+    rn = run(cli, "--gpus", str(n), *cmd, "write", str(tmp_path / "b"))
+    assert r1.returncode == rn.returncode == 101
+    a = np.fromfile(str(tmp_path / "a") + ".sr656250.cf32", dtype=np.uint32)
+    b = np.fromfile(str(tmp_path / "b") + ".sr656250.cf32", dtype=np.uint32)
+    assert np.array_equal(a, b)
