@@ -66,8 +66,10 @@ typedef enum {
 typedef enum {
     QD_SRC_HOST_MEM = 0,   /* raw capture bytes in host memory (what SampleFile preads, samples.rs:72-93) */
     QD_SRC_DEVICE_MEM = 1, /* the same bytes already resident in HBM: pointer aligned to one sample, and the
-                              allocation readable up to the next 16-byte boundary past the last sample (tiles
-                              are fetched by 16-byte-granular bulk copies; any cudaMalloc block satisfies it) */
+                              allocation readable from the 16-byte boundary at or before the first sample up to
+                              the next 16-byte boundary past the last one (tiles are fetched by 16-byte-granular
+                              bulk copies and vector loads; any cudaMalloc block, or a sample-aligned view into
+                              one, satisfies it) */
     QD_SRC_FILE = 2,       /* path; the library preads it */
     QD_SRC_GEN = 3         /* gen.rs */
 } qd_source_kind;

@@ -578,12 +578,19 @@ __device__ __forceinline__ void decode_exact_global(const FirArgs &a, const uint
                                                     float4 *__restrict__ X4, int idx)
 {
     static_assert(STRIDE % Gm::G == 0, "a thread's groups stay in one row");
-    constexpr uint32_t GB = FMT == QD_FMT_CS16 ? 16u : 8u; // bytes per group of 4 samples
-    const uint32_t n_loc = (n_dec + 3) >> 2;
+    constexpr uint32_t GB = FMT == QD_FMT_CF32 ? 32u : (FMT == QD_FMT_CS16 ? 16u : 8u); // bytes per group of 4 samples
+    // integer formats: a partial last group is decoded whole (its bytes lie inside the 16-byte granule the source
+    // contract makes readable); cf32 groups are two granules, so the last 0..3 samples go one at a time
+    const uint32_t n_loc = FMT == QD_FMT_CF32 ? (n_dec >> 2) : ((n_dec + 3) >> 2);
     float4 *xb = X4 + (idx & (Gm::G - 1)) * Gm::PITCH + (idx >> Gm::LOG_G);
     double nd = __ull2double_rn(n0 + static_cast<uint64_t>(4 * idx));
-    auto fetch = [&](uint32_t gc, uint32_t (&w)[4]) {
-        if (FMT == QD_FMT_CS16) {
+    constexpr int NW = FMT == QD_FMT_CF32 ? 8 : 4;
+    auto fetch = [&](uint32_t gc, uint32_t (&w)[NW]) {
+        if (FMT == QD_FMT_CF32) {
+            const uint4 lo = ldg_stream_v4(g0 + static_cast<size_t>(GB) * gc), hi = ldg_stream_v4(g0 + static_cast<size_t>(GB) * gc + 16);
+            w[0] = lo.x, w[1] = lo.y, w[2] = lo.z, w[3] = lo.w;
+            w[NW - 4] = hi.x, w[NW - 3] = hi.y, w[NW - 2] = hi.z, w[NW - 1] = hi.w;
+        } else if (FMT == QD_FMT_CS16) {
             const uint4 v = ldg_stream_v4(g0 + static_cast<size_t>(GB) * gc);
             w[0] = v.x, w[1] = v.y, w[2] = v.z, w[3] = v.w;
         } else {
@@ -591,20 +598,40 @@ __device__ __forceinline__ void decode_exact_global(const FirArgs &a, const uint
             w[0] = v.x, w[1] = v.y, w[2] = 0, w[3] = 0;
         }
     };
-    uint32_t nxt[4] = {0, 0, 0, 0};
+    uint32_t nxt[NW];
+#pragma unroll
+    for (int i = 0; i < NW; i++) nxt[i] = 0;
     if (static_cast<uint32_t>(idx) < n_loc) fetch(idx, nxt);
 #pragma unroll 2
     for (uint32_t gc = idx; gc < n_loc; gc += STRIDE, xb += STRIDE / Gm::G) {
-        const uint32_t cur[4] = {nxt[0], nxt[1], nxt[2], nxt[3]};
+        uint32_t cur[NW];
+#pragma unroll
+        for (int i = 0; i < NW; i++) cur[i] = nxt[i];
         if (gc + STRIDE < n_loc) fetch(gc + STRIDE, nxt);
         float2 x[4];
-        unpack_words<FMT>(cur, x, a.one);
+        if constexpr (FMT == QD_FMT_CF32) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) x[i] = make_float2(__uint_as_float(cur[2 * i]), __uint_as_float(cur[2 * i + 1])); // bit copy, lib.rs:248
+        } else {
+            const uint32_t c4[4] = {cur[0], cur[1], cur[2], cur[3]};
+            unpack_words<FMT>(c4, x, a.one);
+        }
         if (a.n_shift) {
             mix_group_exact(a, x, nd);
             nd = __dadd_rn(nd, static_cast<double>(4 * STRIDE));
         }
         xb[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
         xb[Gm::G * Gm::PITCH] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+    }
+    if (FMT == QD_FMT_CF32 && idx == 0) { // the last 0..3 samples, one at a time
+        for (uint32_t l = 4 * n_loc; l < n_dec; l++) {
+            float2 v = __ldg(reinterpret_cast<const float2 *>(g0) + l);
+            const double ni = __ull2double_rn(n0 + l);
+            for (int sft = 0; sft < a.n_shift; sft++) v = mix_exact<false>(v, ni, a.ratio[sft], a);
+            const uint32_t pr = (l >> 1) & (Gm::DR / 2 - 1);
+            float4 *el = X4 + ((pr & 1) * Gm::G + (pr >> 1)) * Gm::PITCH + (l >> Gm::LOG_DR);
+            reinterpret_cast<float2 *>(el)[l & 1] = v;
+        }
     }
 }
 
@@ -1390,6 +1417,9 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
                 else decode_tile_lean<D, R, NT, LMAX, false>(a, raw, lead, l_lo, n_dec, g.n_tile0, lphase, ttab, X, tid);
             } else if (a.fmt == QD_FMT_CF32 && a.n_shift == 0 && lead == 0 && l_lo == 0) {
                 decode_cf32_copy<Gm, NT>(raw, n_dec, X, tid);
+            } else if (EXACT && a.fmt == QD_FMT_CF32 && lead == 0 && l_lo == 0) {
+                // cf32 behind shifts: the same lean loop as the unstaged integer tiles (packed mixer, next group in flight)
+                decode_exact_global<Gm, NT, QD_FMT_CF32>(a, raw, n_dec, g.n_tile0, reinterpret_cast<float4 *>(X), tid);
             } else if (EXACT && !staged && a.fmt != QD_FMT_CF32 && (lead & 3) == 0 && l_lo == 0) {
                 const uint8_t *g0 = raw + pb * lead;
                 float4 *X4 = reinterpret_cast<float4 *>(X);
