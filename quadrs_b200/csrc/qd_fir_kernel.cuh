@@ -552,12 +552,13 @@ __device__ __forceinline__ void unpack_group(uint32_t rp, float2 (&x)[4], float2
 
 // the reference's mixer on a group of four decoded samples: fl64(n * ratio), an f64 sin/cos per sample and shift
 // (shift.rs:49-50), num-complex's multiply with every product and sum rounded on its own (shift.rs:51)
+template <bool HALF = false>
 __device__ __forceinline__ void mix_group_exact(const FirArgs &a, float2 (&x)[4], double nd)
 {
     const float2 one = a.one;
     auto mix = [&](float2 v, double ni, double ratio) {
         double c, sn;
-        sincos_f64k<false>(__dmul_rn(ni, ratio), a.sincos, a.k, c, sn); // (long-filter kernels: the full table)
+        sincos_f64k<HALF>(__dmul_rn(ni, ratio), a.sincos, a.k, c, sn);
         const float cf = static_cast<float>(c), sf = static_cast<float>(sn);
         const float2 p1 = mul2(make_float2(v.x, v.x), make_float2(cf, sf));
         const float2 p2 = mul2(make_float2(v.y, v.y), make_float2(-sf, cf));
@@ -617,7 +618,7 @@ __device__ __forceinline__ void decode_exact_global(const FirArgs &a, const uint
             unpack_words<FMT>(c4, x, a.one);
         }
         if (a.n_shift) {
-            mix_group_exact(a, x, nd);
+            mix_group_exact<(FMT == QD_FMT_CF32)>(a, x, nd); // (integer tiles of the long-filter kernels: the full table)
             nd = __dadd_rn(nd, static_cast<double>(4 * STRIDE));
         }
         xb[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
