@@ -48,6 +48,53 @@ __device__ __forceinline__ float2 decode_sample(const uint8_t *__restrict__ raw,
     }
 }
 
+// The same values without an integer->float conversion (I2F runs on the 16-lane conversion pipe): a byte or half
+// word dropped into the mantissa of 2^23 by PRMT is the float 2^23 + v, one exact subtraction leaves v, and the
+// quotient / offset steps are the packed forms of div_exact (each half individually rounded: identical bits).
+__device__ __forceinline__ float2 f2_fma(float2 a, float2 b, float2 c)
+{
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 f2_mul(float2 a, float2 b)
+{
+    float2 d;
+    asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+// (one = (1, 1) passed in by the caller as a kernel parameter: opaque to ptxas, so x * 1 + c is not folded)
+template <int FMT>
+__device__ __forceinline__ float2 decode_sample_packed(const uint8_t *__restrict__ raw, uint64_t i, float2 one)
+{
+    if (FMT == 0) return __ldg(reinterpret_cast<const float2 *>(raw) + i); // cf32: bit copy
+    float2 n;
+    float den, c, off;
+    if (FMT == 3) { // cs16
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(raw) + i) ^ 0x80008000u;
+        n = make_float2(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7410)) - 8421376.0f,
+                        __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7432)) - 8421376.0f); // -(2^23 + 32768): exact
+        den = 65535.0f, c = 1.0f / 65535.0f, off = -32767.5f;
+    } else {
+        const uint32_t h = static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short *>(raw) + i)) ^ (FMT == 1 ? 0x8080u : 0u);
+        const float k = FMT == 1 ? 8388736.0f : 8388608.0f; // 2^23 + 128 (cs8, bytes flipped to offset binary) or 2^23
+        n = make_float2(__uint_as_float(__byte_perm(h, 0x4B000000u, 0x7440)) - k, __uint_as_float(__byte_perm(h, 0x4B000000u, 0x7441)) - k);
+        den = FMT == 1 ? 127.0f : 255.0f, c = FMT == 1 ? 1.0f / 127.0f : 1.0f / 255.0f, off = -127.5f;
+    }
+    const float2 c2 = make_float2(c, c);
+    const float2 q0 = f2_mul(n, c2);
+    const float2 r = f2_fma(q0, make_float2(-den, -den), n);
+    const float2 q = f2_fma(r, c2, q0); // the correctly rounded quotient (div_exact)
+    if (FMT == 1) return q;            // lib.rs:251
+    return f2_fma(q, one, make_float2(off, off)); // lib.rs:252-253: one rounding, as the subtraction
+}
+
 // ---- cos/sin of an f64 phase, rounded to f32 (shift.rs:50, gen.rs:41) ---------------------------
 // theta is the reference's own f64 phase.  Reduction by 2 pi/256 is exact (the first FMA's result is
 // representable because |r| < 2^-5 while 2 pi/256 has its last bit at 2^-58); the table is

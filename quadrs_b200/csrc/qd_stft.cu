@@ -45,11 +45,20 @@ __device__ __forceinline__ float2 load_elem(const FftArgs &a, uint64_t u, uint32
 template <int MODE, int N, typename Place>
 __device__ __forceinline__ void load_group_m(const FftArgs &a, uint64_t u, uint32_t first, uint32_t step, float2 *e, Place place)
 {
+    if (MODE < 0) {
+        // the window in the stream, its last tail_len samples in the patch matrix: both bases once per window
+        const float2 *__restrict__ win = a.in + u * a.in_pitch;
+        const uint32_t n_tail = a.W - a.tail_len; // = W without a patch
+        const float2 *__restrict__ tl = a.tail + u * a.tail_len - n_tail;
 #pragma unroll
-    for (int i = 0; i < N; i++) {
-        const uint32_t n = first + step * i;
-        if (MODE < 0) e[place(i)] = (a.tail_len && n >= a.W - a.tail_len) ? a.tail[u * a.tail_len + (n - (a.W - a.tail_len))] : a.in[u * a.in_pitch + n];
-        else e[place(i)] = decode_sample(a.raw, MODE, a.raw_first + u * a.in_pitch + n);
+        for (int i = 0; i < N; i++) {
+            const uint32_t n = first + step * i;
+            e[place(i)] = *((n >= n_tail ? tl : win) + n);
+        }
+    } else {
+        const uint64_t base = a.raw_first + u * a.in_pitch; // first sample of the window
+#pragma unroll
+        for (int i = 0; i < N; i++) e[place(i)] = decode_sample_packed<MODE>(a.raw, base + first + step * i, a.one);
     }
 }
 template <int N, typename Place>

@@ -67,11 +67,15 @@ __device__ __forceinline__ int glyph_fast(const FftArgs &a, float2 v)
     const double x = v.x, y = v.y;
     const double s = fma(x, x, __dmul_rn(y, y));
     const uint32_t sh = static_cast<uint32_t>(__double2hiint(s));
-    const uint32_t c3 = a.thr_hi[3];
+    // (all nine high words once, then selects between registers: an index that depends on a comparison would be a
+    // constant-bank load per use)
+    const uint32_t t0 = a.thr_hi[0], t1 = a.thr_hi[1], t2 = a.thr_hi[2], t3 = a.thr_hi[3], t4 = a.thr_hi[4], t5 = a.thr_hi[5],
+                   t6 = a.thr_hi[6];
+    const uint32_t c3 = t3;
     const bool h3 = sh >= c3;
-    const uint32_t c1 = h3 ? a.thr_hi[5] : a.thr_hi[1];
+    const uint32_t c1 = h3 ? t5 : t1;
     const bool h1 = sh >= c1;
-    const uint32_t c0 = h3 ? (h1 ? a.thr_hi[6] : a.thr_hi[4]) : (h1 ? a.thr_hi[2] : a.thr_hi[0]);
+    const uint32_t c0 = h3 ? (h1 ? t6 : t4) : (h1 ? t2 : t0);
     const int r = (h3 ? 4 : 0) + (h1 ? 2 : 0) + (sh >= c0 ? 1 : 0);
     const uint32_t c8 = a.thr_hi[8], c7 = a.thr_hi[7];
     int g = sh >= c8 ? 8 : (sh >= c7 ? 9 : r);
