@@ -574,3 +574,74 @@ def test_fast_full_size_config2_shards_and_host_path_bitwise(Q):
         h.write_into(0x1000, 0, chunks, h_out.data_ptr(), chunks * 0x1000, Q._lib.SPACE_HOST)
         h.synchronize()
         assert torch.equal(h_out, d_out.cpu()), f"host path, segment_bytes {seg}"
+
+
+# ---------------------------------------------------------------- BASELINE sizes, whole captures
+def _full_size_sparkfft(Q, fmt, rate, total, stages, W, S, rng, synth_args, need, sample_rows):
+    """The whole capture resident on the device: every row computed, sampled rows against the oracle (from the
+    device's own bytes), and a two-shard run equal to the unsharded one in every byte of the output."""
+    import torch
+
+    pb = O.FORMAT_BYTES[fmt]
+    synth = Q.make_synth(*synth_args)
+    d_in = torch.empty(pb * total + 64, dtype=torch.uint8, device="cuda")
+    Q.synth_fill_device(synth, fmt, 0, total, d_in.data_ptr())
+    torch.cuda.synchronize()
+
+    def build(src):
+        for st in stages:
+            src = src.shift(st[1]) if st[0] == "shift" else src.lowpass(st[1], st[2], st[3])
+        return src
+
+    whole = build(Q.Samples.from_device(d_in.data_ptr(), pb * total, fmt, rate, keep=(d_in,)))
+    rows_total = whole.spark_rows(W, S)
+    d_idx = torch.zeros(rows_total * W, dtype=torch.uint8, device="cuda")
+    assert whole.spark_fft_device(W, S, rng, 0, rows_total, d_idx.data_ptr()) == rows_total
+    whole.synchronize()
+    rows = [r if r >= 0 else rows_total + r for r in sample_rows]
+    want = _oracle_rows_from_device(Q, torch, d_in, fmt, rate, total, 0, stages, W, S, rng, rows, need)
+    for r, (widx, _) in zip(rows, want):
+        got = d_idx[r * W : (r + 1) * W].cpu().numpy()
+        assert np.array_equal(got, widx), f"row {r}"
+    assert int(d_idx.max()) <= 8 and int((d_idx > 0).sum()) > 0
+    d_idx2 = torch.zeros_like(d_idx)
+    for r in range(2):
+        p = Q.shard_plan(fmt, rate, total, stages, Q.shard.SINK_SPARKFFT, W, S, 2, r)
+        view = d_in[pb * p.first_sample : pb * (p.first_sample + p.n_samples)]
+        g = build(Q.Samples.from_device(view.data_ptr(), view.numel(), fmt, rate, base_sample=p.first_sample,
+                                        total_samples=total, keep=(d_in,)))
+        assert g.spark_fft_device(W, S, rng, p.first_unit, p.n_units, d_idx2.data_ptr() + p.first_unit * W) == p.n_units
+        g.synchronize()
+    assert torch.equal(d_idx, d_idx2)
+    return rows_total
+
+
+def test_full_size_config3_whole_capture(Q):
+    """BASELINE.json configs[2]: cu8, 2^30 samples, sparkfft -width 4096 -stride 1024 (4 GiB of glyph rows)."""
+    rate = 2_400_000
+    synth = (0x5EED0003, [(Q.tone_step(-800e3, rate), 40, 0), (Q.tone_step(-123_456, rate), 30, 0),
+                          (Q.tone_step(300e3, rate), 25, 0), (Q.tone_step(1_000_001, rate), 20, 0)], 4)
+    rows = _full_size_sparkfft(Q, Q.CU8, rate, 2**30, [], 4096, 1024, (2.0, 500.0), synth, 4096,
+                               [0, 1, 524_287, 524_288, -2, -1])
+    assert rows == (2**30 - 4096 + 1023) // 1024
+
+
+def test_full_size_config4_whole_capture(Q):
+    """BASELINE.json configs[3] at its full 2^33 samples (32 GiB resident): filter and STFT in one kernel."""
+    rate = 100_000_000
+    st = [("shift", 7_000_000), ("lowpass", 2_000_000, 16, 800)]
+    synth = (0x5EED0004, [(Q.tone_step(7.3e6, rate), 9000, 0), (Q.tone_step(6.2e6, rate), 6000, 50_000),
+                          (Q.tone_step(-20e6, rate), 4000, 0)], 1200)
+    rows = _full_size_sparkfft(Q, Q.CS16, rate, 2**33, st, 128, 128, (0.5, 50.0), synth, 128 * 16 + 800,
+                               [0, 1, 2_097_151, 2_097_152, 3_333_333, -2, -1])
+    assert rows == 4_194_303
+
+
+def test_full_size_config5_whole_buffer(Q):
+    """BASELINE.json configs[4] on the resident 2^32-sample buffer the bench uses (32 GiB): two lowpasses, 4-point windows."""
+    rate = 400_000_000
+    st = [("lowpass", 20_000_000, 8, 40), ("lowpass", 500_000, 32, 40)]
+    synth = (0x5EED0005, [(Q.tone_step(0.1e6, rate), 160, 1_000_000), (Q.tone_step(90e6, rate), 3000, 0)], 40)
+    rows = _full_size_sparkfft(Q, Q.CF32, rate, 2**32, st, 4, 2, (0.001, 0.01), synth, (4 * 32 + 40) * 8 + 40,
+                               [0, 1, 2, 4_194_303, 4_194_304, -2, -1])
+    assert rows > 8_000_000
