@@ -20,6 +20,7 @@
 #include <unistd.h>
 
 #include "qd_fir_kernel.cuh"
+#include "qd_tcfir.h"
 
 namespace qd {
 
@@ -39,7 +40,9 @@ struct TailArgs {
     uint32_t log_d;         // D = 2^log_d
     uint32_t wpw;           // windows per warp: min(32 / T, 8)
     uint64_t off0, S, n_call, n_units;
-    float2 *out; // [n_units][T]
+    float2 *out; // tail r of window u at out[u * out_pitch + out_off + r]: a patch matrix [n_units][T] (pitch T, offset 0)
+                 // or the tails' own places in a [n_units][n_call] output (pitch n_call, offset n_call - T)
+    uint64_t out_pitch, out_off;
     float2 one;
 };
 constexpr int kTailWarps = 4;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(32 * kTailWarps) fk_tail(const __grid_constant
         const float2 *xg = x + g * pitch;
         float2 acc = make_float2(0.0f, 0.0f);
         for (uint32_t j = 0, l = r * a.D; j < J; j++, l++) acc = fma2(mul2(xg[l + (l >> a.log_d)], taps.t[j]), a.one, acc); // fl(acc + fl(x * f)), filter.rs:119
-        a.out[(u0 + g) * a.T + r] = acc;
+        a.out[(u0 + g) * a.out_pitch + a.out_off + r] = acc;
     }
 }
 
@@ -318,6 +321,86 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     return set_error(QD_E_INVALID_ARG, "internal: no fused FIR for decimate %u", D);
 }
 
+// The truncated tails of nu windows (off0 + u*S, n_call) in the exact arithmetic, each at out[u*pitch + off + r]
+static int launch_tail(Chain &c, const LpInfo &top, int fmt, int n_shift, const double *ratios, const uint8_t *d_src, uint64_t src_base,
+                       uint64_t off0, uint64_t S, uint64_t n_call, uint64_t nu, float2 *out, uint64_t pitch, uint64_t off)
+{
+    TailArgs ta;
+    memset(&ta, 0, sizeof ta);
+    ta.src = d_src;
+    ta.src_base = src_base;
+    ta.fmt = fmt;
+    ta.n_shift = n_shift;
+    for (int i = 0; i < n_shift; i++) ta.ratio[i] = ratios[i];
+    ta.sincos = c.ctx->d_sincos;
+    ta.L = top.L, ta.D = top.D, ta.T = top.T;
+    ta.span = top.T * top.D + top.L / 2;
+    ta.log_d = 0;
+    while ((1u << ta.log_d) < top.D) ta.log_d++;
+    ta.off0 = off0, ta.S = S, ta.n_call = n_call, ta.n_units = nu;
+    ta.out = out;
+    ta.out_pitch = pitch, ta.out_off = off;
+    ta.one = make_float2(1.0f, 1.0f);
+    FirTaps tt;
+    memset(&tt, 0, sizeof tt);
+    for (uint32_t i = 0; i < top.L; i++) tt.t[i] = make_float2(top.st->taps[i], top.st->taps[i]);
+    ta.wpw = std::max<uint32_t>(1, std::min<uint32_t>(32 / top.T, 8));
+    const size_t tsm = static_cast<size_t>(kTailWarps) * ta.wpw * (ta.span + (ta.span >> ta.log_d) + 1) * sizeof(float2);
+    if (tsm > 48 * 1024) QD_CUDA(cudaFuncSetAttribute(fk_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tsm)));
+    const uint64_t per_cta = static_cast<uint64_t>(kTailWarps) * ta.wpw;
+    fk_tail<<<static_cast<unsigned>((nu + per_cta - 1) / per_cta), 32 * kTailWarps, tsm, c.stream>>>(ta, tt);
+    QD_LAUNCHED();
+    return QD_OK;
+}
+
+// FAST arithmetic over a cs8 capture, units that tile the output stream: the filter runs on the tensor cores
+// (fk_tcfir) as one untruncated stream, and the T truncated outputs at the end of every unit are then written over
+// by fk_tail.  *done = false: the shape is not one the tensor-core kernel takes.
+static int run_tc(Chain &c, const FastPlan &f, const double *ratios, const uint8_t *d_src, uint64_t src_base, uint64_t src_end,
+                  uint64_t soff, uint64_t unit_len, uint64_t stride, uint64_t nu, float2 *d_out, bool *done)
+{
+    *done = false;
+    const LpInfo &top = f.lp[0];
+    if (!c.use_tc || c.precision != QD_PRECISION_FAST || c.src.format != QD_FMT_CS8 || f.n_lp != 1 || f.stream_top) return QD_OK;
+    if (nu > 1 && stride != unit_len) return QD_OK;
+    if (top.T > 32 || top.T >= unit_len) return QD_OK;
+    TcGeom g;
+    if (!tcfir_geometry(top.L, top.D, &g)) return QD_OK;
+    double rsum = 0.0, rabs = 0.0;
+    for (int i = 0; i < f.n_shift; i++) rsum += ratios[i], rabs += fabs(ratios[i]);
+    // The reference mixes with cos/sin of fl64(n * ratio) (shift.rs:49), which is off the exact product by up to half
+    // an ulp of n * ratio; the CUDA-core FAST kernel re-applies that per-sample rounding, a matrix product cannot.  It
+    // is taken only while that phase error stays below 2^-25 rad (3e-8: n * ratio < 2^29, e.g. config 2's 2^30 samples),
+    // where it is two orders of magnitude below the 1e-5 tolerance even on an output 60 dB under the input.
+    {
+        int ex = 0;
+        frexp(static_cast<double>(src_end) * rabs, &ex);
+        if (rabs != 0.0 && ex > 29) return QD_OK;
+    }
+    uint64_t key[4] = {top.L, top.D, 0, 0};
+    memcpy(&key[2], &rsum, 8);
+    for (uint32_t j = 0; j < top.L; j++) {
+        uint32_t b;
+        memcpy(&b, &top.st->taps[j], 4);
+        key[3] = key[3] * 0x9E3779B97F4A7C15ull + b;
+    }
+    if (!c.tc_bimg.p || memcmp(key, c.tc_key, sizeof key) != 0) {
+        QD_CUDA(cudaStreamSynchronize(c.stream)); // an earlier launch may still read the old image
+        tcfir_b_image(g, top.st->taps.data(), top.L, top.D, rsum, c.tc_host, &c.tc_s_hi, &c.tc_s_lo);
+        QD_TRY(c.ensure(c.tc_bimg, c.tc_host.size()));
+        QD_CUDA(cudaMemcpyAsync(c.tc_bimg.p, c.tc_host.data(), c.tc_host.size(), cudaMemcpyHostToDevice, c.stream));
+        QD_CUDA(cudaStreamSynchronize(c.stream));
+        memcpy(c.tc_key, key, sizeof key);
+    }
+    QD_TRY(launch_tcfir(c, g, static_cast<const uint8_t *>(c.tc_bimg.p), c.tc_s_hi, c.tc_s_lo, top.L, top.D, f.n_shift, ratios, d_src,
+                        src_base, src_end, soff, soff + nu * unit_len, d_out));
+    if (top.T > 0)
+        QD_TRY(launch_tail(c, top, c.src.format, f.n_shift, ratios, d_src, src_base, soff, unit_len, unit_len, nu, d_out, unit_len,
+                           unit_len - top.T));
+    *done = true;
+    return QD_OK;
+}
+
 // Number of leading units of the arithmetic progression off0 + u*stride that are FULL: the read
 // returns unit_len samples and its raw span lies inside the capture (so only the per-unit
 // truncation rule applies, never the end-of-file one).
@@ -439,6 +522,7 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
 
         const float2 *d_top;
         uint64_t pitch;
+        bool tc_done = false; // the segment's filter ran on the tensor cores (fk_tcfir)
         QD_TRY(c.prof_begin());
         // sparkfft over back-to-back windows behind a run-time-length filter in EXACT arithmetic: the STFT runs inside
         // the filter kernel (whole windows per tile, window starts on multiples of R), nothing but glyph rows is written
@@ -462,8 +546,10 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
                 QD_TRY(c.ensure(c.pipe_out[j], nu * unit_len * sizeof(float2)));
                 d_out = static_cast<float2 *>(c.pipe_out[j].p);
             }
-            QD_TRY(launch_fir(c, top, s.format, f.n_shift, ratios, d_src, src_base, src_end, soff, unit_len, stride, nu,
-                              nu * unit_len, d_out));
+            QD_TRY(run_tc(c, f, ratios, d_src, src_base, src_end, soff, unit_len, stride, nu, d_out, &tc_done));
+            if (!tc_done)
+                QD_TRY(launch_fir(c, top, s.format, f.n_shift, ratios, d_src, src_base, src_end, soff, unit_len, stride, nu,
+                                  nu * unit_len, d_out));
             d_top = d_out;
             pitch = unit_len;
         } else {
@@ -545,34 +631,13 @@ int run_units_fast(Chain &c, uint64_t off0, uint64_t stride, uint64_t n_units, u
             }
             d_top = d_out;
             pitch = stride;
-            if (f.stream_tail && !snap_tails) {
-                TailArgs ta;
-                memset(&ta, 0, sizeof ta);
-                ta.src = d_src;
-                ta.src_base = src_base;
-                ta.fmt = s.format;
-                ta.n_shift = f.n_shift;
-                for (int i = 0; i < f.n_shift; i++) ta.ratio[i] = ratios[i];
-                ta.sincos = c.ctx->d_sincos;
-                ta.L = top.L, ta.D = top.D, ta.T = top.T;
-                ta.span = top.T * top.D + top.L / 2;
-                ta.log_d = 0;
-                while ((1u << ta.log_d) < top.D) ta.log_d++;
-                ta.off0 = soff, ta.S = stride, ta.n_call = unit_len, ta.n_units = nu;
-                ta.out = static_cast<float2 *>(c.pipe_tail[j].p);
-                ta.one = make_float2(1.0f, 1.0f);
-                FirTaps tt;
-                memset(&tt, 0, sizeof tt);
-                for (uint32_t i = 0; i < top.L; i++) tt.t[i] = make_float2(top.st->taps[i], top.st->taps[i]);
-                ta.wpw = std::max<uint32_t>(1, std::min<uint32_t>(32 / top.T, 8));
-                const size_t tsm = static_cast<size_t>(kTailWarps) * ta.wpw * (ta.span + (ta.span >> ta.log_d) + 1) * sizeof(float2);
-                if (tsm > 48 * 1024) QD_CUDA(cudaFuncSetAttribute(fk_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(tsm)));
-                const uint64_t per_cta = static_cast<uint64_t>(kTailWarps) * ta.wpw;
-                fk_tail<<<static_cast<unsigned>((nu + per_cta - 1) / per_cta), 32 * kTailWarps, tsm, c.stream>>>(ta, tt);
-                QD_LAUNCHED();
-            }
+            if (f.stream_tail && !snap_tails)
+                QD_TRY(launch_tail(c, top, s.format, f.n_shift, ratios, d_src, src_base, soff, stride, unit_len, nu,
+                                   static_cast<float2 *>(c.pipe_tail[j].p), top.T, 0));
         }
-        QD_TRY(c.prof_end(fuse ? "fk_fir (fused decode+mix+FIR-decimate+STFT+glyphs)" : "fk_fir (fused decode+mix+FIR-decimate)"));
+        QD_TRY(c.prof_end(fuse      ? "fk_fir (fused decode+mix+FIR-decimate+STFT+glyphs)"
+                          : tc_done ? "fk_tcfir (tensor-core decode+mix+FIR-decimate) + fk_tail"
+                                    : "fk_fir (fused decode+mix+FIR-decimate)"));
         QD_CUDA(cudaEventRecord(c.ev_compute[j], c.stream)); // the raw staging buffer may be refilled
         if (on_segment) {
             const int rc = on_segment(c, user, j, u0, nu, d_top, pitch);

@@ -269,6 +269,7 @@ Chain::~Chain()
     rel(twiddles);
     rel(window);
     rel(flag);
+    rel(tc_bimg);
     for (int j = 0; j < 2; j++) {
         rel(pipe_in[j]);
         rel(pipe_mid[j]);

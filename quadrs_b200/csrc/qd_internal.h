@@ -154,6 +154,13 @@ struct Chain {
     bool use_fast = true;
     int fuse_stft = 1; // sparkfft inside the filter kernel: 0 never, 1 for back-to-back windows (stride = width), 2 also for
                        // overlapping windows and two-stage chains (measured slower than the separate kernels: qd_fast.cu)
+    // FAST arithmetic over cs8 captures: the filter runs on the tensor cores (fk_tcfir, qd_tcfir.cu) when the chain's
+    // shape allows; 0 keeps the CUDA-core kernel
+    int use_tc = 1;
+    Buf tc_bimg;                  // B operand image of the current filter
+    std::vector<uint8_t> tc_host; // its host copy (source of the upload)
+    uint64_t tc_key[4] = {0, 0, 0, 0}; // (L, D, bits of the ratio sum, tap checksum) the image was built for
+    float tc_s_hi = 0.0f, tc_s_lo = 0.0f;
     int fir_cta_cap = 0; // experiments: resident fk_fir CTAs per SM (0 = as many as fit)
     size_t segment_bytes = size_t(32) << 20; // raw bytes staged per segment for host / file sources (measured best of 16..256 MiB)
     bool pipeline_ready = false;
