@@ -16,8 +16,8 @@
 // row phasor (one f64 sin/cos per row, from the table the exact mixer uses) and sums the 1 + (NOUT-1)/OPR rows that
 // meet in an output, in ascending row order.
 //
-// Roles (one persistent CTA per SM, 13 warps): warps 0-3 epilogue (TMEM lane quarter = warp index), warp 4 TMEM
-// allocation + the single MMA-issuing thread, warps 5-12 producers: coalesced 16-byte loads of raw bytes, int8 ->
+// Roles (one persistent CTA per SM, 21 warps): warps 0-3 epilogue (TMEM lane quarter = warp index), warp 4 TMEM
+// allocation + the single MMA-issuing thread, warps 5-20 producers: coalesced 16-byte loads of raw bytes, int8 ->
 // f16 by PRMT into the mantissa of 1024 (no I2F), 128B-swizzled K-major stores, fence.proxy.async, mbarrier arrive.
 #include <cuda_fp16.h>
 
@@ -34,7 +34,7 @@ namespace qd {
 constexpr int kTcRows = 128;           // rows (of 64 samples) per MMA tile = UMMA M
 constexpr int kTcRowSamples = 64;      // K = 128 reals = two 128-byte swizzle atoms of f16
 constexpr int kTcEpiWarps = 4;
-constexpr int kTcProdWarps = 8;
+constexpr int kTcProdWarps = 16;
 constexpr int kTcThreads = 32 * (kTcEpiWarps + 1 + kTcProdWarps);
 constexpr uint32_t kTcStageBytes = 2 * kTcRows * 128; // one tile of A: two K atoms of 128 rows x 128 bytes
 
@@ -49,6 +49,7 @@ struct TcArgs {
     int n_shift;
     double ratio[4];
     const double *sincos;
+    SinCosK k;
     float s_hi, s_lo;
     int64_t row_first; // first row of tile 0
     uint32_t rows_eff; // rows a tile finalises: 128 - (DMAX - 1)
@@ -130,8 +131,13 @@ __device__ __forceinline__ uint4 tc_load_chunk(const TcArgs &a, int64_t n)
     return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// OPR_/NOUT_ != 0: the row geometry is known at compile time (the reference's default filter, args.rs:165: 40 taps,
+// at decimate 8), so the epilogue keeps a row's partials in registers and is fully unrolled; 0/0: any geometry, the
+// partials go through shared memory.
+template <int OPR_, int NOUT_>
 __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant__ TcArgs a)
 {
+    constexpr bool FIXED = OPR_ != 0;
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~uintptr_t(1023));
     TcHeader *hd = reinterpret_cast<TcHeader *>(smem);
@@ -167,57 +173,123 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = hd->tmem_base;
+    // tiles of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const uint32_t n_my = blockIdx.x < a.n_tiles ? (a.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
     if (warp < kTcEpiWarps) {
         // ================= epilogue: TMEM -> partials -> row rotation -> sum over the rows of an output -> global
         const int r = warp * 32 + lane; // tile row = TMEM lane
-        uint32_t it = 0;
-        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t acc = it & 1, aph = (it >> 1) & 1;
+        const uint32_t opr = FIXED ? OPR_ : a.OPR, nout = FIXED ? NOUT_ : a.NOUT, nh = FIXED ? (2 * NOUT_ + 7) / 8 * 8 : a.NH;
+        const uint32_t xp = FIXED ? ((2 * NOUT_) | 1) : a.XP;
+        for (uint32_t k = 0; k < n_my; k++) {
+            const uint32_t tile = blockIdx.x + k * gridDim.x;
+            const uint32_t acc = k & 1, aph = (k >> 1) & 1;
             const int64_t b = a.row_first + static_cast<int64_t>(tile) * a.rows_eff + r;
             // the row phasor e^{i ratio 64 b}: the product of the shifts' phasors at sample 64 b, as the mixer forms them
             float2 rot = make_float2(1.0f, 0.0f);
             for (int s = 0; s < a.n_shift; s++) {
-                const float2 p = phasor_exact(static_cast<uint64_t>(b < 0 ? 0 : b) * kTcRowSamples, a.ratio[s], a.sincos);
-                rot = make_float2(rot.x * p.x - rot.y * p.y, rot.x * p.y + rot.y * p.x);
+                const double place = __dmul_rn(__ll2double_rn(b * kTcRowSamples), a.ratio[s]); // shift.rs:49
+                double cd, sd;
+                sincos_f64k<false>(place, a.sincos, a.k, cd, sd);
+                const float2 p = make_float2(static_cast<float>(cd), static_cast<float>(sd));
+                rot = s == 0 ? p : make_float2(rot.x * p.x - rot.y * p.y, rot.x * p.y + rot.y * p.x);
             }
+            float *xr = sX + static_cast<size_t>(k & 1) * kTcRows * xp + static_cast<size_t>(r) * xp;
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * a.acc_cols;
+            const int64_t gbase = static_cast<int64_t>(opr) * b + a.cown;
+            float2 *o = a.out + (gbase - static_cast<int64_t>(a.g0));
+            // every own output of every finalising row of the tile lies inside [g0, g1)?
+            const int64_t g_lo = static_cast<int64_t>(opr) * (b - r) + a.cown, g_hi = g_lo + static_cast<int64_t>(opr) * a.rows_eff;
+            const bool inside = g_lo >= static_cast<int64_t>(a.g0) && g_hi <= static_cast<int64_t>(a.g1);
             mbar_wait(&hd->acc_full[acc], aph);
             tc_fence_after();
-            float *xr = sX + static_cast<size_t>(it & 1) * kTcRows * a.XP + static_cast<size_t>(r) * a.XP;
-            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * a.acc_cols;
-            for (uint32_t c = 0; c < a.NH; c += 8) {
-                float hi[8], lo[8];
-                tc_ld8(t0 + c, hi);
-                tc_ld8(t0 + a.NH + c, lo);
-                tc_wait_ld();
+            if constexpr (FIXED) {
+                constexpr int NC = 2 * NOUT_, NH = (2 * NOUT_ + 7) / 8 * 8;
+                float part[NC];
 #pragma unroll
-                for (int k = 0; k < 8; k += 2) {
-                    const float pr = hi[k] * a.s_hi + lo[k] * a.s_lo, pi = hi[k + 1] * a.s_hi + lo[k + 1] * a.s_lo;
-                    if (c + k < 2 * a.NOUT) {
-                        xr[c + k] = pr * rot.x - pi * rot.y;
-                        xr[c + k + 1] = pr * rot.y + pi * rot.x;
+                for (int c = 0; c < NH; c += 8) {
+                    float hi[8], lo[8];
+                    tc_ld8(t0 + c, hi);
+                    tc_ld8(t0 + NH + c, lo);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 8; q++)
+                        if (c + q < NC) part[c + q] = hi[q] * a.s_hi + lo[q] * a.s_lo;
+                }
+                tc_fence_before(); // the accumulator may be overwritten by the tile after next
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hd->acc_empty[acc]);
+#pragma unroll
+                for (int i = 0; i < NOUT_; i++) {
+                    const float pr = part[2 * i], pi = part[2 * i + 1];
+                    part[2 * i] = pr * rot.x - pi * rot.y;
+                    part[2 * i + 1] = pr * rot.y + pi * rot.x;
+                }
+                // what the rows below need of this row: its partials for outputs that start in earlier rows
+#pragma unroll
+                for (int i = 0; i < 2 * (NOUT_ - OPR_); i++) xr[i] = part[i];
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (static_cast<uint32_t>(r) < a.rows_eff) {
+                    float2 y[OPR_];
+#pragma unroll
+                    for (int t = 0; t < OPR_; t++) {
+                        y[t] = make_float2(part[2 * (NOUT_ - OPR_ + t)], part[2 * (NOUT_ - OPR_ + t) + 1]);
+#pragma unroll
+                        for (int d = 1; d * OPR_ < NOUT_; d++) {
+                            const int ip = NOUT_ - OPR_ * (d + 1) + t;
+                            if (ip >= 0) {
+                                y[t].x += xr[d * ((2 * NOUT_) | 1) + 2 * ip];
+                                y[t].y += xr[d * ((2 * NOUT_) | 1) + 2 * ip + 1];
+                            }
+                        }
+                    }
+                    if (inside) {
+                        if ((reinterpret_cast<uintptr_t>(o) & 15) == 0 && OPR_ % 2 == 0) {
+#pragma unroll
+                            for (int t = 0; t < OPR_; t += 2)
+                                *reinterpret_cast<float4 *>(o + t) = make_float4(y[t].x, y[t].y, y[t + 1].x, y[t + 1].y);
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < OPR_; t++) o[t] = y[t];
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < OPR_; t++)
+                            if (gbase + t >= static_cast<int64_t>(a.g0) && gbase + t < static_cast<int64_t>(a.g1)) o[t] = y[t];
                     }
                 }
-            }
-            // the accumulator may be overwritten by the tile after next
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hd->acc_empty[acc]);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-            if (static_cast<uint32_t>(r) < a.rows_eff) {
-                const int64_t gbase = static_cast<int64_t>(a.OPR) * b + a.cown;
-                for (uint32_t t = 0; t < a.OPR; t++) {
-                    const int64_t g = gbase + t;
-                    if (g < static_cast<int64_t>(a.g0) || g >= static_cast<int64_t>(a.g1)) continue;
-                    float yr = 0.0f, yi = 0.0f;
-                    for (uint32_t d = 0; d < a.DMAX; d++) {
-                        const int32_t ip = static_cast<int32_t>(a.NOUT) - static_cast<int32_t>(a.OPR * (d + 1)) + static_cast<int32_t>(t);
-                        if (ip < 0) break;
-                        const float *p = xr + static_cast<size_t>(d) * a.XP + 2 * ip;
-                        yr += p[0];
-                        yi += p[1];
+            } else {
+                for (uint32_t c = 0; c < nh; c += 8) {
+                    float hi[8], lo[8];
+                    tc_ld8(t0 + c, hi);
+                    tc_ld8(t0 + nh + c, lo);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int q = 0; q < 8; q += 2) {
+                        const float pr = hi[q] * a.s_hi + lo[q] * a.s_lo, pi = hi[q + 1] * a.s_hi + lo[q + 1] * a.s_lo;
+                        if (c + q < 2 * nout) {
+                            xr[c + q] = pr * rot.x - pi * rot.y;
+                            xr[c + q + 1] = pr * rot.y + pi * rot.x;
+                        }
                     }
-                    a.out[g - static_cast<int64_t>(a.g0)] = make_float2(yr, yi);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hd->acc_empty[acc]);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (static_cast<uint32_t>(r) < a.rows_eff) {
+                    for (uint32_t t = 0; t < opr; t++) {
+                        if (!inside && (gbase + t < static_cast<int64_t>(a.g0) || gbase + t >= static_cast<int64_t>(a.g1))) continue;
+                        float yr = 0.0f, yi = 0.0f;
+                        for (uint32_t d = 0; d < a.DMAX; d++) {
+                            const int32_t ip = static_cast<int32_t>(nout) - static_cast<int32_t>(opr * (d + 1)) + static_cast<int32_t>(t);
+                            if (ip < 0) break;
+                            const float *p = xr + d * xp + 2 * ip;
+                            yr += p[0];
+                            yi += p[1];
+                        }
+                        o[t] = make_float2(yr, yi);
+                    }
                 }
             }
         }
@@ -225,9 +297,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
         // ================= MMA issue (one thread)
         const uint32_t idesc = (1u << 4) | ((a.N >> 3) << 17) | ((kTcRows >> 4) << 24); // f16 x f16 -> f32, K-major A and B
         const uint32_t b_base = smem_u32(sB);
-        uint32_t it = 0;
-        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t st = it % a.stages, ph = (it / a.stages) & 1, acc = it & 1, aph = (it >> 1) & 1;
+        for (uint32_t k = 0; k < n_my; k++) {
+            const uint32_t st = k % a.stages, ph = (k / a.stages) & 1, acc = k & 1, aph = (k >> 1) & 1;
             mbar_wait(&hd->acc_empty[acc], aph ^ 1);
             mbar_wait(&hd->full[st], ph);
             tc_fence_after();
@@ -247,45 +318,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
             __syncwarp();
         }
     } else {
-        // ================= producers: raw bytes -> f16 A tile (K-major, 128-byte swizzle)
+        // ================= producers: raw bytes -> f16 A tile (K-major, 128-byte swizzle), loads kPf - 1 tiles ahead
+        constexpr int kPf = 4, kPer = kTcRows * 8 / (32 * kTcProdWarps); // 16-byte chunks per thread and tile
         const int pw = warp - kTcEpiWarps - 1;
         const uint32_t row4 = 2 * (lane >> 4) + ((lane >> 2) & 1), ka = (lane >> 3) & 1, cp = lane & 3;
-        uint32_t it = 0;
-        uint4 cur[4];
-        auto load_tile = [&](uint32_t tile, uint4 *v) {
-            const int64_t b0 = a.row_first + static_cast<int64_t>(tile) * a.rows_eff;
+        uint4 buf[kPf][kPer];
+        auto load_tile = [&](uint32_t k, uint4(&v)[kPer]) {
+            const int64_t b0 = a.row_first + static_cast<int64_t>(blockIdx.x + k * gridDim.x) * a.rows_eff;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < kPer; i++) {
                 const uint32_t row = 4 * (i * kTcProdWarps + pw) + row4;
                 v[i] = tc_load_chunk(a, (b0 + row) * kTcRowSamples + 8 * (ka * 4 + cp));
             }
         };
-        if (blockIdx.x < a.n_tiles) load_tile(blockIdx.x, cur);
-        for (uint32_t tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++it) {
-            const uint32_t st = it % a.stages, ph = (it / a.stages) & 1;
-            uint4 nxt[4];
-            const uint32_t tn = tile + gridDim.x;
-            if (tn < a.n_tiles) load_tile(tn, nxt);
-            mbar_wait(&hd->empty[st], ph ^ 1);
-            uint8_t *stage = sA + static_cast<size_t>(st) * kTcStageBytes + ka * (kTcRows * 128);
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const uint32_t row = 4 * (i * kTcProdWarps + pw) + row4;
-                uint4 lo4, hi4;
-                cvt_s8x4(cur[i].x, lo4.x, lo4.y);
-                cvt_s8x4(cur[i].y, lo4.z, lo4.w);
-                cvt_s8x4(cur[i].z, hi4.x, hi4.y);
-                cvt_s8x4(cur[i].w, hi4.z, hi4.w);
-                uint8_t *rowp = stage + row * 128;
-                *reinterpret_cast<uint4 *>(rowp + (((2 * cp) ^ (row & 7)) << 4)) = lo4;
-                *reinterpret_cast<uint4 *>(rowp + (((2 * cp + 1) ^ (row & 7)) << 4)) = hi4;
-            }
-            fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hd->full[st]);
-            if (tn < a.n_tiles) {
+        for (int u = 0; u < kPf - 1; u++)
+            if (static_cast<uint32_t>(u) < n_my) load_tile(u, buf[u]);
+        for (uint32_t k0 = 0; k0 < n_my; k0 += kPf) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) cur[i] = nxt[i];
+            for (int u = 0; u < kPf; u++) {
+                const uint32_t k = k0 + u;
+                if (k >= n_my) break;
+                if (k + kPf - 1 < n_my) load_tile(k + kPf - 1, buf[(u + kPf - 1) % kPf]);
+                const uint32_t st = k % a.stages, ph = (k / a.stages) & 1;
+                mbar_wait(&hd->empty[st], ph ^ 1);
+                uint8_t *stage = sA + static_cast<size_t>(st) * kTcStageBytes + ka * (kTcRows * 128);
+#pragma unroll
+                for (int i = 0; i < kPer; i++) {
+                    const uint32_t row = 4 * (i * kTcProdWarps + pw) + row4;
+                    const uint4 v = buf[u][i];
+                    uint4 lo4, hi4;
+                    cvt_s8x4(v.x, lo4.x, lo4.y);
+                    cvt_s8x4(v.y, lo4.z, lo4.w);
+                    cvt_s8x4(v.z, hi4.x, hi4.y);
+                    cvt_s8x4(v.w, hi4.z, hi4.w);
+                    uint8_t *rowp = stage + row * 128;
+                    *reinterpret_cast<uint4 *>(rowp + (((2 * cp) ^ (row & 7)) << 4)) = lo4;
+                    *reinterpret_cast<uint4 *>(rowp + (((2 * cp + 1) ^ (row & 7)) << 4)) = hi4;
+                }
+                fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hd->full[st]);
             }
         }
     }
@@ -379,6 +452,7 @@ int launch_tcfir(Chain &c, const TcGeom &g, const uint8_t *d_bimg, float s_hi, f
     a.n_shift = n_shift;
     for (int i = 0; i < n_shift; i++) a.ratio[i] = ratios[i];
     a.sincos = c.ctx->d_sincos;
+    a.k = make_sincos_k();
     a.s_hi = s_hi, a.s_lo = s_lo;
     // output g is finalised by the row that holds its first sample g*D + i0
     const int64_t i0 = L - L / 2;
@@ -399,9 +473,14 @@ int launch_tcfir(Chain &c, const TcGeom &g, const uint8_t *d_bimg, float s_hi, f
     if (a.off_a + kTcStageBytes > cap) return set_error(QD_E_INVALID_ARG, "internal: tensor-core FIR does not fit shared memory");
     a.stages = std::min<uint32_t>(4, (cap - a.off_a) / kTcStageBytes);
     const size_t smem = 1024 + a.off_a + static_cast<size_t>(a.stages) * kTcStageBytes;
-    QD_CUDA(cudaFuncSetAttribute(fk_tcfir, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, static_cast<uint64_t>(c.ctx->sm_count)));
-    fk_tcfir<<<grid, kTcThreads, smem, c.stream>>>(a);
+    if (g.OPR == 8 && g.NOUT == 13) { // the reference's default filter (40 taps) at decimate 8: config 2
+        QD_CUDA(cudaFuncSetAttribute(fk_tcfir<8, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        fk_tcfir<8, 13><<<grid, kTcThreads, smem, c.stream>>>(a);
+    } else {
+        QD_CUDA(cudaFuncSetAttribute(fk_tcfir<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        fk_tcfir<0, 0><<<grid, kTcThreads, smem, c.stream>>>(a);
+    }
     QD_LAUNCHED();
     return QD_OK;
 }
