@@ -16,8 +16,8 @@
 // row phasor (one f64 sin/cos per row, from the table the exact mixer uses) and sums the 1 + (NOUT-1)/OPR rows that
 // meet in an output, in ascending row order.
 //
-// Roles (one persistent CTA per SM, 21 warps): warps 0-3 epilogue (TMEM lane quarter = warp index), warp 4 TMEM
-// allocation + the single MMA-issuing thread, warps 5-20 producers: coalesced 16-byte loads of raw bytes, int8 ->
+// Roles (one persistent CTA per SM, 25 warps): warps 0-7 epilogue (two groups of four taking alternate tiles, TMEM
+// lane quarter = warp & 3), warp 8 TMEM allocation + the single MMA-issuing thread, warps 9-24 producers: coalesced 16-byte loads of raw bytes, int8 ->
 // f16 by PRMT into the mantissa of 1024 (no I2F), 128B-swizzled K-major stores, fence.proxy.async, mbarrier arrive.
 #include <cuda_fp16.h>
 
@@ -33,10 +33,11 @@ namespace qd {
 
 constexpr int kTcRows = 128;           // rows (of 64 samples) per MMA tile = UMMA M
 constexpr int kTcRowSamples = 64;      // K = 128 reals = two 128-byte swizzle atoms of f16
-constexpr int kTcEpiWarps = 4;
+constexpr int kTcEpiWarps = 8;           // two groups of four (TMEM lane quarter = warp & 3) taking alternate tiles
 constexpr int kTcProdWarps = 16;
 constexpr int kTcThreads = 32 * (kTcEpiWarps + 1 + kTcProdWarps);
 constexpr uint32_t kTcStageBytes = 2 * kTcRows * 128; // one tile of A: two K atoms of 128 rows x 128 bytes
+constexpr uint32_t kTcStages = 4;
 
 struct TcArgs {
     const uint8_t *src; // device pointer to raw sample src_base (absolute sample 0 sits on a 16-byte boundary)
@@ -61,6 +62,19 @@ struct TcArgs {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// mbarrier wait whose polls may be suspended by the hardware (time hint): a waiting role must not spend issue slots
+__device__ __forceinline__ void mbar_wait_tc(uint64_t *bar, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+                 "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(parity), "r"(0x989680u)
+                 : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint4 v)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -148,13 +162,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
 
     // ---- setup: barriers, TMEM, the B image
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < a.stages; s++) {
+        for (uint32_t s = 0; s < kTcStages; s++) {
             mbar_init(&hd->full[s], kTcProdWarps);
             mbar_init(&hd->empty[s], 1);
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(&hd->acc_full[s], 1);
-            mbar_init(&hd->acc_empty[s], kTcEpiWarps);
+            mbar_init(&hd->acc_empty[s], kTcEpiWarps / 2);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -178,12 +192,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
 
     if (warp < kTcEpiWarps) {
         // ================= epilogue: TMEM -> partials -> row rotation -> sum over the rows of an output -> global
-        const int r = warp * 32 + lane; // tile row = TMEM lane
+        // group `grp` takes the CTA's tiles grp, grp + 2, ...: accumulator stage = grp
+        const int grp = warp >> 2, quarter = warp & 3;
+        const int r = quarter * 32 + lane; // tile row = TMEM lane
         const uint32_t opr = FIXED ? OPR_ : a.OPR, nout = FIXED ? NOUT_ : a.NOUT, nh = FIXED ? (2 * NOUT_ + 7) / 8 * 8 : a.NH;
-        const uint32_t xp = FIXED ? ((2 * NOUT_) | 1) : a.XP;
-        for (uint32_t k = 0; k < n_my; k++) {
+        // exchange of partials between the rows of a tile: FIXED keeps a row's own partials in registers and double
+        // buffers what its neighbours need; the general path passes everything and closes a tile with a second barrier
+        const uint32_t xp = FIXED ? ((2 * (NOUT_ - OPR_)) | 1) : a.XP;
+        for (uint32_t k = grp; k < n_my; k += 2) {
             const uint32_t tile = blockIdx.x + k * gridDim.x;
-            const uint32_t acc = k & 1, aph = (k >> 1) & 1;
+            const uint32_t acc = grp, aph = (k >> 1) & 1;
             const int64_t b = a.row_first + static_cast<int64_t>(tile) * a.rows_eff + r;
             // the row phasor e^{i ratio 64 b}: the product of the shifts' phasors at sample 64 b, as the mixer forms them
             float2 rot = make_float2(1.0f, 0.0f);
@@ -194,14 +212,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                 const float2 p = make_float2(static_cast<float>(cd), static_cast<float>(sd));
                 rot = s == 0 ? p : make_float2(rot.x * p.x - rot.y * p.y, rot.x * p.y + rot.y * p.x);
             }
-            float *xr = sX + static_cast<size_t>(k & 1) * kTcRows * xp + static_cast<size_t>(r) * xp;
-            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(warp * 32) << 16) + acc * a.acc_cols;
+            float *xr = sX + static_cast<size_t>(FIXED ? 2 * grp + ((k >> 1) & 1) : grp) * kTcRows * xp + static_cast<size_t>(r) * xp;
+            const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * a.acc_cols;
             const int64_t gbase = static_cast<int64_t>(opr) * b + a.cown;
             float2 *o = a.out + (gbase - static_cast<int64_t>(a.g0));
             // every own output of every finalising row of the tile lies inside [g0, g1)?
             const int64_t g_lo = static_cast<int64_t>(opr) * (b - r) + a.cown, g_hi = g_lo + static_cast<int64_t>(opr) * a.rows_eff;
             const bool inside = g_lo >= static_cast<int64_t>(a.g0) && g_hi <= static_cast<int64_t>(a.g1);
-            mbar_wait(&hd->acc_full[acc], aph);
+            mbar_wait_tc(&hd->acc_full[acc], aph);
             tc_fence_after();
             if constexpr (FIXED) {
                 constexpr int NC = 2 * NOUT_, NH = (2 * NOUT_ + 7) / 8 * 8;
@@ -228,7 +246,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                 // what the rows below need of this row: its partials for outputs that start in earlier rows
 #pragma unroll
                 for (int i = 0; i < 2 * (NOUT_ - OPR_); i++) xr[i] = part[i];
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                 if (static_cast<uint32_t>(r) < a.rows_eff) {
                     float2 y[OPR_];
 #pragma unroll
@@ -238,8 +256,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                         for (int d = 1; d * OPR_ < NOUT_; d++) {
                             const int ip = NOUT_ - OPR_ * (d + 1) + t;
                             if (ip >= 0) {
-                                y[t].x += xr[d * ((2 * NOUT_) | 1) + 2 * ip];
-                                y[t].y += xr[d * ((2 * NOUT_) | 1) + 2 * ip + 1];
+                                y[t].x += xr[d * ((2 * (NOUT_ - OPR_)) | 1) + 2 * ip];
+                                y[t].y += xr[d * ((2 * (NOUT_ - OPR_)) | 1) + 2 * ip + 1];
                             }
                         }
                     }
@@ -276,7 +294,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hd->acc_empty[acc]);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                 if (static_cast<uint32_t>(r) < a.rows_eff) {
                     for (uint32_t t = 0; t < opr; t++) {
                         if (!inside && (gbase + t < static_cast<int64_t>(a.g0) || gbase + t >= static_cast<int64_t>(a.g1))) continue;
@@ -291,6 +309,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                         o[t] = make_float2(yr, yi);
                     }
                 }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); // the exchange buffer is free again
             }
         }
     } else if (warp == kTcEpiWarps) {
@@ -298,9 +317,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
         const uint32_t idesc = (1u << 4) | ((a.N >> 3) << 17) | ((kTcRows >> 4) << 24); // f16 x f16 -> f32, K-major A and B
         const uint32_t b_base = smem_u32(sB);
         for (uint32_t k = 0; k < n_my; k++) {
-            const uint32_t st = k % a.stages, ph = (k / a.stages) & 1, acc = k & 1, aph = (k >> 1) & 1;
-            mbar_wait(&hd->acc_empty[acc], aph ^ 1);
-            mbar_wait(&hd->full[st], ph);
+            const uint32_t st = k % kTcStages, ph = (k / kTcStages) & 1, acc = k & 1, aph = (k >> 1) & 1;
+            mbar_wait_tc(&hd->acc_empty[acc], aph ^ 1);
+            mbar_wait_tc(&hd->full[st], ph);
             tc_fence_after();
             if (lane == 0) {
                 const uint32_t a_base = smem_u32(sA + static_cast<size_t>(st) * kTcStageBytes);
@@ -323,12 +342,26 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
         const int pw = warp - kTcEpiWarps - 1;
         const uint32_t row4 = 2 * (lane >> 4) + ((lane >> 2) & 1), ka = (lane >> 3) & 1, cp = lane & 3;
         uint4 buf[kPf][kPer];
-        auto load_tile = [&](uint32_t k, uint4(&v)[kPer]) {
-            const int64_t b0 = a.row_first + static_cast<int64_t>(blockIdx.x + k * gridDim.x) * a.rows_eff;
+        // per-thread constants: byte offset of its chunks inside a tile's raw bytes, and where their two 16-byte f16
+        // halves go inside a stage
+        uint32_t g_off[kPer], s_off[kPer][2];
 #pragma unroll
-            for (int i = 0; i < kPer; i++) {
-                const uint32_t row = 4 * (i * kTcProdWarps + pw) + row4;
-                v[i] = tc_load_chunk(a, (b0 + row) * kTcRowSamples + 8 * (ka * 4 + cp));
+        for (int i = 0; i < kPer; i++) {
+            const uint32_t row = 4 * (i * kTcProdWarps + pw) + row4;
+            g_off[i] = row * 128 + 16 * (ka * 4 + cp);
+            s_off[i][0] = ka * (kTcRows * 128) + row * 128 + (((2 * cp) ^ (row & 7)) << 4);
+            s_off[i][1] = ka * (kTcRows * 128) + row * 128 + (((2 * cp + 1) ^ (row & 7)) << 4);
+        }
+        const uint32_t sA_u32 = smem_u32(sA);
+        auto load_tile = [&](uint32_t k, uint4(&v)[kPer]) {
+            const int64_t n0 = (a.row_first + static_cast<int64_t>(blockIdx.x + k * gridDim.x) * a.rows_eff) * kTcRowSamples;
+            if (n0 >= static_cast<int64_t>(a.src_base) && n0 + kTcRows * kTcRowSamples <= static_cast<int64_t>(a.src_end)) {
+                const uint8_t *tp = a.src + (n0 - static_cast<int64_t>(a.src_base)) * 2; // the tile's 16 KB are contiguous
+#pragma unroll
+                for (int i = 0; i < kPer; i++) v[i] = ldg_stream_v4(tp + g_off[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kPer; i++) v[i] = tc_load_chunk(a, n0 + (g_off[i] >> 1));
             }
         };
 #pragma unroll
@@ -340,21 +373,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                 const uint32_t k = k0 + u;
                 if (k >= n_my) break;
                 if (k + kPf - 1 < n_my) load_tile(k + kPf - 1, buf[(u + kPf - 1) % kPf]);
-                const uint32_t st = k % a.stages, ph = (k / a.stages) & 1;
-                mbar_wait(&hd->empty[st], ph ^ 1);
-                uint8_t *stage = sA + static_cast<size_t>(st) * kTcStageBytes + ka * (kTcRows * 128);
+                const uint32_t st = k % kTcStages, ph = (k / kTcStages) & 1;
+                mbar_wait_tc(&hd->empty[st], ph ^ 1);
+                const uint32_t stage = sA_u32 + st * kTcStageBytes;
 #pragma unroll
                 for (int i = 0; i < kPer; i++) {
-                    const uint32_t row = 4 * (i * kTcProdWarps + pw) + row4;
                     const uint4 v = buf[u][i];
                     uint4 lo4, hi4;
                     cvt_s8x4(v.x, lo4.x, lo4.y);
                     cvt_s8x4(v.y, lo4.z, lo4.w);
                     cvt_s8x4(v.z, hi4.x, hi4.y);
                     cvt_s8x4(v.w, hi4.z, hi4.w);
-                    uint8_t *rowp = stage + row * 128;
-                    *reinterpret_cast<uint4 *>(rowp + (((2 * cp) ^ (row & 7)) << 4)) = lo4;
-                    *reinterpret_cast<uint4 *>(rowp + (((2 * cp + 1) ^ (row & 7)) << 4)) = hi4;
+                    sts_v4(stage + s_off[i][0], lo4);
+                    sts_v4(stage + s_off[i][1], hi4);
                 }
                 fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
                 __syncwarp();
@@ -392,6 +423,11 @@ bool tcfir_geometry(uint32_t L, uint32_t D, TcGeom *g)
     if (g->DMAX >= 64) return false;
     g->cown = g->c0 + static_cast<int32_t>(g->NOUT) - static_cast<int32_t>(g->OPR);
     g->XP = (2 * g->NOUT) | 1;
+    // B image + exchange buffers + the A stages must fit one CTA's shared memory (tcfir_smem_layout)
+    const bool fixed = g->OPR == 8 && g->NOUT == 13;
+    const uint32_t x_bytes = fixed ? 4 * kTcRows * ((2 * (g->NOUT - g->OPR)) | 1) * 4 : 2 * kTcRows * g->XP * 4;
+    const uint32_t off_a = (1024 + 2 * g->N * 128 + x_bytes + 1023) / 1024 * 1024;
+    if (off_a + kTcStages * kTcStageBytes > 227 * 1024 - 1024) return false;
     return true;
 }
 
@@ -467,14 +503,16 @@ int launch_tcfir(Chain &c, const TcGeom &g, const uint8_t *d_bimg, float s_hi, f
     while (a.tmem_cols < 2 * a.acc_cols) a.tmem_cols *= 2;
     a.off_b = 1024;
     a.off_x = a.off_b + 2 * g.N * 128;
-    const uint32_t x_bytes = 2 * kTcRows * g.XP * 4;
+    const bool fixed = g.OPR == 8 && g.NOUT == 13; // the reference's default filter (40 taps) at decimate 8: config 2
+    const uint32_t x_bytes = fixed ? 4 * kTcRows * ((2 * (g.NOUT - g.OPR)) | 1) * 4 : 2 * kTcRows * g.XP * 4;
     a.off_a = (a.off_x + x_bytes + 1023) / 1024 * 1024;
     const uint32_t cap = 227 * 1024 - 1024;
     if (a.off_a + kTcStageBytes > cap) return set_error(QD_E_INVALID_ARG, "internal: tensor-core FIR does not fit shared memory");
-    a.stages = std::min<uint32_t>(4, (cap - a.off_a) / kTcStageBytes);
-    const size_t smem = 1024 + a.off_a + static_cast<size_t>(a.stages) * kTcStageBytes;
+    if (a.off_a + kTcStages * kTcStageBytes > cap) return set_error(QD_E_INVALID_ARG, "internal: tensor-core FIR does not fit shared memory");
+    a.stages = kTcStages;
+    const size_t smem = 1024 + a.off_a + static_cast<size_t>(kTcStages) * kTcStageBytes;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, static_cast<uint64_t>(c.ctx->sm_count)));
-    if (g.OPR == 8 && g.NOUT == 13) { // the reference's default filter (40 taps) at decimate 8: config 2
+    if (fixed) {
         QD_CUDA(cudaFuncSetAttribute(fk_tcfir<8, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         fk_tcfir<8, 13><<<grid, kTcThreads, smem, c.stream>>>(a);
     } else {
