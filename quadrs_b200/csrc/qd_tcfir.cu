@@ -16,9 +16,11 @@
 // row phasor (one f64 sin/cos per row, from the table the exact mixer uses) and sums the 1 + (NOUT-1)/OPR rows that
 // meet in an output, in ascending row order.
 //
-// Roles (one persistent CTA per SM, 25 warps): warps 0-7 epilogue (two groups of four taking alternate tiles, TMEM
-// lane quarter = warp & 3), warp 8 TMEM allocation + the single MMA-issuing thread, warps 9-24 producers: coalesced 16-byte loads of raw bytes, int8 ->
-// f16 by PRMT into the mantissa of 1024 (no I2F), 128B-swizzled K-major stores, fence.proxy.async, mbarrier arrive.
+// Roles (one persistent CTA per SM, 26 warps): warps 0-7 epilogue (two groups of four taking alternate tiles, TMEM
+// lane quarter = warp & 3); warp 8 TMEM allocation + the single MMA-issuing thread; warp 9 one thread issuing 16 KB
+// bulk copies (TMA) of the tiles' raw bytes into a ring of up to 8 slots (~100 KB of loads in flight per SM); warp 10
+// the tiles' f64 phase anchors; warps 11-26 converters: raw bytes from the ring, int8 -> f16 by PRMT into the mantissa of 1024 (no
+// I2F), 128B-swizzled K-major stores, fence.proxy.async, mbarrier arrive.
 #include <cuda_fp16.h>
 
 #include <cmath>
@@ -35,9 +37,12 @@ constexpr int kTcRows = 128;           // rows (of 64 samples) per MMA tile = UM
 constexpr int kTcRowSamples = 64;      // K = 128 reals = two 128-byte swizzle atoms of f16
 constexpr int kTcEpiWarps = 8;           // two groups of four (TMEM lane quarter = warp & 3) taking alternate tiles
 constexpr int kTcProdWarps = 16;
-constexpr int kTcThreads = 32 * (kTcEpiWarps + 1 + kTcProdWarps);
+constexpr int kTcThreads = 32 * (kTcEpiWarps + 3 + kTcProdWarps);
 constexpr uint32_t kTcStageBytes = 2 * kTcRows * 128; // one tile of A: two K atoms of 128 rows x 128 bytes
-constexpr uint32_t kTcStages = 4;
+constexpr uint32_t kTcStages = 2;
+constexpr uint32_t kTcRawBytes = kTcRows * kTcRowSamples * 2; // a tile's raw cs8 bytes: 16 KB, contiguous in the capture
+constexpr uint32_t kTcRawMax = 8;
+constexpr uint32_t kTcAnchors = 32; // ring of per-tile phase anchors, filled 16 tiles at a time
 
 struct TcArgs {
     const uint8_t *src; // device pointer to raw sample src_base (absolute sample 0 sits on a 16-byte boundary)
@@ -55,7 +60,8 @@ struct TcArgs {
     int64_t row_first; // first row of tile 0
     uint32_t rows_eff; // rows a tile finalises: 128 - (DMAX - 1)
     uint32_t n_tiles, stages, acc_cols, tmem_cols;
-    uint32_t off_b, off_x, off_a; // byte offsets inside (1024-aligned) dynamic shared memory
+    uint32_t off_b, off_x, off_a, off_raw; // byte offsets inside (1024-aligned) dynamic shared memory
+    uint32_t raw_slots;                    // depth of the raw-byte ring the bulk copies fill
 };
 
 // ---------------------------------------------------------------------------- PTX
@@ -100,6 +106,29 @@ __device__ __forceinline__ void tc_ld8(uint32_t taddr, float *v)
 #pragma unroll
     for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, float *v)
+{
+    uint32_t r[16];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float2 lds_f2(uint32_t saddr)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(saddr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f2(uint32_t saddr, float2 v)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(saddr), "f"(v.x), "f"(v.y) : "memory");
+}
+// e^{i sum_s fl64(n ratio_s)} in f64: the product of the shifts' phasors at sample n, each phase formed as shift.rs:49 does
+__device__ __forceinline__ double2 tc_phasor64(const TcArgs &a, int64_t n);
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand, 128-byte swizzle: 8-row groups of 128-byte rows, 1024 bytes apart (SBO); LBO unused; version 1
@@ -111,9 +140,12 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr)
 
 // Shared-memory header (at the 1024-aligned base): barriers and the TMEM base address
 struct TcHeader {
-    uint64_t full[4], empty[4], acc_full[2], acc_empty[2];
+    uint64_t full[4], empty[4], acc_full[2], acc_empty[2], raw_full[kTcRawMax], raw_empty[kTcRawMax], anc_full[kTcAnchors], anc_empty[kTcAnchors];
     uint32_t tmem_base;
+    alignas(16) double2 anchor[kTcAnchors][2]; // per tile: e^{i ratio 64 * 128 q} for the two 128-row groups q the tile's rows lie in
+    double2 w[kTcRows];            // e^{i ratio 64 r}, r < 128
 };
+static_assert(sizeof(TcHeader) <= 4096, "header region");
 
 // four int8 I/Q bytes (two complex samples) -> two half2 (re, im): byte + 128 dropped into the mantissa of 1024.0h is
 // the half 1024 + 128 + x; one exact packed subtraction leaves x
@@ -125,6 +157,18 @@ __device__ __forceinline__ void cvt_s8x4(uint32_t w, uint32_t &h0, uint32_t &h1)
     const __half2 ra = __hsub2(*reinterpret_cast<const __half2 *>(&a), k), rb = __hsub2(*reinterpret_cast<const __half2 *>(&b), k);
     h0 = *reinterpret_cast<const uint32_t *>(&ra);
     h1 = *reinterpret_cast<const uint32_t *>(&rb);
+}
+
+__device__ __forceinline__ double2 tc_phasor64(const TcArgs &a, int64_t n)
+{
+    double2 w = make_double2(1.0, 0.0);
+    for (int s = 0; s < a.n_shift; s++) {
+        const double place = __dmul_rn(__ll2double_rn(n), a.ratio[s]);
+        double cd, sd;
+        sincos_f64k<false>(place, a.sincos, a.k, cd, sd);
+        w = s == 0 ? make_double2(cd, sd) : make_double2(w.x * cd - w.y * sd, w.x * sd + w.y * cd);
+    }
+    return w;
 }
 
 // 16 raw bytes (8 samples from absolute sample n) of the capture, zero where the capture does not hold them
@@ -166,6 +210,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
             mbar_init(&hd->full[s], kTcProdWarps);
             mbar_init(&hd->empty[s], 1);
         }
+        for (uint32_t s = 0; s < kTcRawMax; s++) {
+            mbar_init(&hd->raw_full[s], 1);
+            mbar_init(&hd->raw_empty[s], kTcProdWarps);
+        }
+        for (uint32_t s = 0; s < kTcAnchors; s++) {
+            mbar_init(&hd->anc_full[s], 1);
+            mbar_init(&hd->anc_empty[s], kTcEpiWarps / 2);
+        }
         for (int s = 0; s < 2; s++) {
             mbar_init(&hd->acc_full[s], 1);
             mbar_init(&hd->acc_empty[s], kTcEpiWarps / 2);
@@ -183,6 +235,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
         for (uint32_t i = threadIdx.x; i < nb; i += kTcThreads) s[i] = __ldg(g + i);
         fence_proxy_async();
     }
+    if (threadIdx.x < kTcRows) hd->w[threadIdx.x] = tc_phasor64(a, static_cast<int64_t>(threadIdx.x) * kTcRowSamples);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -198,21 +251,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
         const uint32_t opr = FIXED ? OPR_ : a.OPR, nout = FIXED ? NOUT_ : a.NOUT, nh = FIXED ? (2 * NOUT_ + 7) / 8 * 8 : a.NH;
         // exchange of partials between the rows of a tile: FIXED keeps a row's own partials in registers and double
         // buffers what its neighbours need; the general path passes everything and closes a tile with a second barrier
-        const uint32_t xp = FIXED ? ((2 * (NOUT_ - OPR_)) | 1) : a.XP;
+        const uint32_t xp = a.XP; // (general path; FIXED addresses its own layout)
         for (uint32_t k = grp; k < n_my; k += 2) {
             const uint32_t tile = blockIdx.x + k * gridDim.x;
             const uint32_t acc = grp, aph = (k >> 1) & 1;
             const int64_t b = a.row_first + static_cast<int64_t>(tile) * a.rows_eff + r;
-            // the row phasor e^{i ratio 64 b}: the product of the shifts' phasors at sample 64 b, as the mixer forms them
-            float2 rot = make_float2(1.0f, 0.0f);
-            for (int s = 0; s < a.n_shift; s++) {
-                const double place = __dmul_rn(__ll2double_rn(b * kTcRowSamples), a.ratio[s]); // shift.rs:49
-                double cd, sd;
-                sincos_f64k<false>(place, a.sincos, a.k, cd, sd);
-                const float2 p = make_float2(static_cast<float>(cd), static_cast<float>(sd));
-                rot = s == 0 ? p : make_float2(rot.x * p.x - rot.y * p.y, rot.x * p.y + rot.y * p.x);
+            // The row phasor e^{i ratio 64 b} as a pure function of the absolute row: (anchor of the row's 128-row group,
+            // computed for this tile by the bulk-copy warp) x (e^{i ratio 64 (b mod 128)}, tabulated at kernel start),
+            // one f64 complex product rounded to f32.  s_hi rides along.
+            float2 rot;
+            {
+                const int64_t b0 = b - r;
+                mbar_wait_tc(&hd->anc_full[k % kTcAnchors], (k / kTcAnchors) & 1);
+                const double2 an = hd->anchor[k % kTcAnchors][(b >> 7) - (b0 >> 7)], w = hd->w[b & 127];
+                rot = make_float2(static_cast<float>(an.x * w.x - an.y * w.y) * a.s_hi, static_cast<float>(an.x * w.y + an.y * w.x) * a.s_hi);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hd->anc_empty[k % kTcAnchors]);
             }
-            float *xr = sX + static_cast<size_t>(FIXED ? 2 * grp + ((k >> 1) & 1) : grp) * kTcRows * xp + static_cast<size_t>(r) * xp;
+            float *xr = sX + static_cast<size_t>(grp) * kTcRows * xp + static_cast<size_t>(r) * xp;
             const uint32_t t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * a.acc_cols;
             const int64_t gbase = static_cast<int64_t>(opr) * b + a.cown;
             float2 *o = a.out + (gbase - static_cast<int64_t>(a.g0));
@@ -222,17 +278,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
             mbar_wait_tc(&hd->acc_full[acc], aph);
             tc_fence_after();
             if constexpr (FIXED) {
-                constexpr int NC = 2 * NOUT_, NH = (2 * NOUT_ + 7) / 8 * 8;
+                constexpr int NC = 2 * NOUT_, NH = (2 * NOUT_ + 7) / 8 * 8, XPF = 2 * (NOUT_ - OPR_) + 2;
                 float part[NC];
+                if constexpr (NH % 16 == 0) {
 #pragma unroll
-                for (int c = 0; c < NH; c += 8) {
-                    float hi[8], lo[8];
-                    tc_ld8(t0 + c, hi);
-                    tc_ld8(t0 + NH + c, lo);
-                    tc_wait_ld();
+                    for (int c = 0; c < NH; c += 16) {
+                        float hi[16], lo[16];
+                        tc_ld16(t0 + c, hi);
+                        tc_ld16(t0 + NH + c, lo);
+                        tc_wait_ld();
 #pragma unroll
-                    for (int q = 0; q < 8; q++)
-                        if (c + q < NC) part[c + q] = hi[q] * a.s_hi + lo[q] * a.s_lo;
+                        for (int q = 0; q < 16; q++)
+                            if (c + q < NC) part[c + q] = fmaf(lo[q], 0x1p-11f, hi[q]);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NH; c += 8) {
+                        float hi[8], lo[8];
+                        tc_ld8(t0 + c, hi);
+                        tc_ld8(t0 + NH + c, lo);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            if (c + q < NC) part[c + q] = fmaf(lo[q], 0x1p-11f, hi[q]);
+                    }
                 }
                 tc_fence_before(); // the accumulator may be overwritten by the tile after next
                 __syncwarp();
@@ -244,8 +313,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                     part[2 * i + 1] = pr * rot.y + pi * rot.x;
                 }
                 // what the rows below need of this row: its partials for outputs that start in earlier rows
+                const uint32_t xs = smem_u32(sX) + ((2 * grp + ((k >> 1) & 1)) * kTcRows + r) * (XPF * 4);
 #pragma unroll
-                for (int i = 0; i < 2 * (NOUT_ - OPR_); i++) xr[i] = part[i];
+                for (int i = 0; i < NOUT_ - OPR_; i++) sts_f2(xs + 8 * i, make_float2(part[2 * i], part[2 * i + 1]));
                 asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
                 if (static_cast<uint32_t>(r) < a.rows_eff) {
                     float2 y[OPR_];
@@ -256,8 +326,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                         for (int d = 1; d * OPR_ < NOUT_; d++) {
                             const int ip = NOUT_ - OPR_ * (d + 1) + t;
                             if (ip >= 0) {
-                                y[t].x += xr[d * ((2 * (NOUT_ - OPR_)) | 1) + 2 * ip];
-                                y[t].y += xr[d * ((2 * (NOUT_ - OPR_)) | 1) + 2 * ip + 1];
+                                const float2 v = lds_f2(xs + d * (XPF * 4) + 8 * ip);
+                                y[t].x += v.x;
+                                y[t].y += v.y;
                             }
                         }
                     }
@@ -284,7 +355,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                     tc_wait_ld();
 #pragma unroll
                     for (int q = 0; q < 8; q += 2) {
-                        const float pr = hi[q] * a.s_hi + lo[q] * a.s_lo, pi = hi[q + 1] * a.s_hi + lo[q + 1] * a.s_lo;
+                        const float pr = fmaf(lo[q], 0x1p-11f, hi[q]), pi = fmaf(lo[q + 1], 0x1p-11f, hi[q + 1]);
                         if (c + q < 2 * nout) {
                             xr[c + q] = pr * rot.x - pi * rot.y;
                             xr[c + q + 1] = pr * rot.y + pi * rot.x;
@@ -336,12 +407,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
             }
             __syncwarp();
         }
+    } else if (warp == kTcEpiWarps + 1) {
+        // ================= bulk copies (one thread): a tile's 16 KB of raw bytes -> the raw ring (TMA, no registers)
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0;
+            for (uint32_t k = 0; k < n_my; k++) {
+                mbar_wait_tc(&hd->raw_empty[slot], ph ^ 1);
+                const int64_t n0 = (a.row_first + static_cast<int64_t>(blockIdx.x + k * gridDim.x) * a.rows_eff) * kTcRowSamples;
+                if (n0 >= static_cast<int64_t>(a.src_base) && n0 + kTcRows * kTcRowSamples <= static_cast<int64_t>(a.src_end)) {
+                    mbar_expect_tx(&hd->raw_full[slot], kTcRawBytes);
+                    bulk_g2s(smem + a.off_raw + slot * kTcRawBytes, a.src + (n0 - static_cast<int64_t>(a.src_base)) * 2, kTcRawBytes, &hd->raw_full[slot]);
+                } else {
+                    mbar_arrive(&hd->raw_full[slot]); // a tile at the edge of the capture: the converters read it themselves
+                }
+                if (++slot == a.raw_slots) slot = 0, ph ^= 1;
+            }
+        }
+    } else if (warp == kTcEpiWarps + 2) {
+        // ================= phase anchors: for every tile, e^{i ratio 64 * 128 q} (f64, the phase formed as shift.rs:49
+        // does) of the two 128-row groups q its rows lie in, a ring ahead of the epilogue
+        // (16 tiles per pass: lane l takes tile k0 + l/2, group l & 1)
+        for (uint32_t k0 = 0; k0 < n_my; k0 += 16) {
+            const uint32_t k = min(k0 + (lane >> 1), n_my - 1);
+            const bool valid = k0 + (lane >> 1) < n_my;
+            const int64_t b0 = a.row_first + static_cast<int64_t>(blockIdx.x + k * gridDim.x) * a.rows_eff;
+            const double2 an = tc_phasor64(a, ((b0 >> 7) + (lane & 1)) * (128 * kTcRowSamples));
+            mbar_wait_tc(&hd->anc_empty[k % kTcAnchors], ((k / kTcAnchors) & 1) ^ 1);
+            if (valid) hd->anchor[k % kTcAnchors][lane & 1] = an;
+            __syncwarp();
+            if (valid && (lane & 1) == 0) mbar_arrive(&hd->anc_full[k % kTcAnchors]);
+        }
     } else {
-        // ================= producers: raw bytes -> f16 A tile (K-major, 128-byte swizzle), loads kPf - 1 tiles ahead
-        constexpr int kPf = 4, kPer = kTcRows * 8 / (32 * kTcProdWarps); // 16-byte chunks per thread and tile
-        const int pw = warp - kTcEpiWarps - 1;
+        // ================= converters: raw bytes -> f16 A tile (K-major, 128-byte swizzle)
+        constexpr int kPer = kTcRows * 8 / (32 * kTcProdWarps); // 16-byte chunks per thread and tile
+        const int pw = warp - kTcEpiWarps - 3;
         const uint32_t row4 = 2 * (lane >> 4) + ((lane >> 2) & 1), ka = (lane >> 3) & 1, cp = lane & 3;
-        uint4 buf[kPf][kPer];
         // per-thread constants: byte offset of its chunks inside a tile's raw bytes, and where their two 16-byte f16
         // halves go inside a stage
         uint32_t g_off[kPer], s_off[kPer][2];
@@ -352,45 +452,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
             s_off[i][0] = ka * (kTcRows * 128) + row * 128 + (((2 * cp) ^ (row & 7)) << 4);
             s_off[i][1] = ka * (kTcRows * 128) + row * 128 + (((2 * cp + 1) ^ (row & 7)) << 4);
         }
-        const uint32_t sA_u32 = smem_u32(sA);
-        auto load_tile = [&](uint32_t k, uint4(&v)[kPer]) {
+        const uint32_t sA_u32 = smem_u32(sA), raw_u32 = smem_u32(smem + a.off_raw);
+        uint32_t slot = 0, rph = 0;
+        for (uint32_t k = 0; k < n_my; k++) {
+            const uint32_t st = k % kTcStages, ph = (k / kTcStages) & 1;
+            uint4 v[kPer];
             const int64_t n0 = (a.row_first + static_cast<int64_t>(blockIdx.x + k * gridDim.x) * a.rows_eff) * kTcRowSamples;
-            if (n0 >= static_cast<int64_t>(a.src_base) && n0 + kTcRows * kTcRowSamples <= static_cast<int64_t>(a.src_end)) {
-                const uint8_t *tp = a.src + (n0 - static_cast<int64_t>(a.src_base)) * 2; // the tile's 16 KB are contiguous
+            const bool whole = n0 >= static_cast<int64_t>(a.src_base) && n0 + kTcRows * kTcRowSamples <= static_cast<int64_t>(a.src_end);
+            mbar_wait_tc(&hd->raw_full[slot], rph);
+            if (whole) {
 #pragma unroll
-                for (int i = 0; i < kPer; i++) v[i] = ldg_stream_v4(tp + g_off[i]);
+                for (int i = 0; i < kPer; i++)
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
+                                 : "r"(raw_u32 + slot * kTcRawBytes + g_off[i])
+                                 : "memory");
             } else {
 #pragma unroll
                 for (int i = 0; i < kPer; i++) v[i] = tc_load_chunk(a, n0 + (g_off[i] >> 1));
             }
-        };
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hd->raw_empty[slot]); // the slot's bytes are in registers: it may be refilled
+            if (++slot == a.raw_slots) slot = 0, rph ^= 1;
+            mbar_wait_tc(&hd->empty[st], ph ^ 1);
+            const uint32_t stage = sA_u32 + st * kTcStageBytes;
 #pragma unroll
-        for (int u = 0; u < kPf - 1; u++)
-            if (static_cast<uint32_t>(u) < n_my) load_tile(u, buf[u]);
-        for (uint32_t k0 = 0; k0 < n_my; k0 += kPf) {
-#pragma unroll
-            for (int u = 0; u < kPf; u++) {
-                const uint32_t k = k0 + u;
-                if (k >= n_my) break;
-                if (k + kPf - 1 < n_my) load_tile(k + kPf - 1, buf[(u + kPf - 1) % kPf]);
-                const uint32_t st = k % kTcStages, ph = (k / kTcStages) & 1;
-                mbar_wait_tc(&hd->empty[st], ph ^ 1);
-                const uint32_t stage = sA_u32 + st * kTcStageBytes;
-#pragma unroll
-                for (int i = 0; i < kPer; i++) {
-                    const uint4 v = buf[u][i];
-                    uint4 lo4, hi4;
-                    cvt_s8x4(v.x, lo4.x, lo4.y);
-                    cvt_s8x4(v.y, lo4.z, lo4.w);
-                    cvt_s8x4(v.z, hi4.x, hi4.y);
-                    cvt_s8x4(v.w, hi4.z, hi4.w);
-                    sts_v4(stage + s_off[i][0], lo4);
-                    sts_v4(stage + s_off[i][1], hi4);
-                }
-                fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&hd->full[st]);
+            for (int i = 0; i < kPer; i++) {
+                uint4 lo4, hi4;
+                cvt_s8x4(v[i].x, lo4.x, lo4.y);
+                cvt_s8x4(v[i].y, lo4.z, lo4.w);
+                cvt_s8x4(v[i].z, hi4.x, hi4.y);
+                cvt_s8x4(v[i].w, hi4.z, hi4.w);
+                sts_v4(stage + s_off[i][0], lo4);
+                sts_v4(stage + s_off[i][1], hi4);
             }
+            fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hd->full[st]);
         }
     }
 
@@ -425,9 +523,9 @@ bool tcfir_geometry(uint32_t L, uint32_t D, TcGeom *g)
     g->XP = (2 * g->NOUT) | 1;
     // B image + exchange buffers + the A stages must fit one CTA's shared memory (tcfir_smem_layout)
     const bool fixed = g->OPR == 8 && g->NOUT == 13;
-    const uint32_t x_bytes = fixed ? 4 * kTcRows * ((2 * (g->NOUT - g->OPR)) | 1) * 4 : 2 * kTcRows * g->XP * 4;
-    const uint32_t off_a = (1024 + 2 * g->N * 128 + x_bytes + 1023) / 1024 * 1024;
-    if (off_a + kTcStages * kTcStageBytes > 227 * 1024 - 1024) return false;
+    const uint32_t x_bytes = fixed ? 4 * kTcRows * (2 * (g->NOUT - g->OPR) + 2) * 4 : 2 * kTcRows * g->XP * 4;
+    const uint32_t off_a = (4096 + 2 * g->N * 128 + x_bytes + 1023) / 1024 * 1024;
+    if (off_a + kTcStages * kTcStageBytes + 2 * kTcRawBytes > 227 * 1024 - 1024) return false;
     return true;
 }
 
@@ -501,16 +599,17 @@ int launch_tcfir(Chain &c, const TcGeom &g, const uint8_t *d_bimg, float s_hi, f
     a.acc_cols = g.N;
     a.tmem_cols = 32;
     while (a.tmem_cols < 2 * a.acc_cols) a.tmem_cols *= 2;
-    a.off_b = 1024;
+    a.off_b = 4096;
     a.off_x = a.off_b + 2 * g.N * 128;
     const bool fixed = g.OPR == 8 && g.NOUT == 13; // the reference's default filter (40 taps) at decimate 8: config 2
-    const uint32_t x_bytes = fixed ? 4 * kTcRows * ((2 * (g.NOUT - g.OPR)) | 1) * 4 : 2 * kTcRows * g.XP * 4;
+    const uint32_t x_bytes = fixed ? 4 * kTcRows * (2 * (g.NOUT - g.OPR) + 2) * 4 : 2 * kTcRows * g.XP * 4;
     a.off_a = (a.off_x + x_bytes + 1023) / 1024 * 1024;
     const uint32_t cap = 227 * 1024 - 1024;
-    if (a.off_a + kTcStageBytes > cap) return set_error(QD_E_INVALID_ARG, "internal: tensor-core FIR does not fit shared memory");
-    if (a.off_a + kTcStages * kTcStageBytes > cap) return set_error(QD_E_INVALID_ARG, "internal: tensor-core FIR does not fit shared memory");
+    a.off_raw = a.off_a + kTcStages * kTcStageBytes;
+    if (a.off_raw + 2 * kTcRawBytes > cap) return set_error(QD_E_INVALID_ARG, "internal: tensor-core FIR does not fit shared memory");
     a.stages = kTcStages;
-    const size_t smem = 1024 + a.off_a + static_cast<size_t>(kTcStages) * kTcStageBytes;
+    a.raw_slots = std::min<uint32_t>(kTcRawMax, (cap - a.off_raw) / kTcRawBytes);
+    const size_t smem = 1024 + a.off_raw + static_cast<size_t>(a.raw_slots) * kTcRawBytes;
     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(tiles, static_cast<uint64_t>(c.ctx->sm_count)));
     if (fixed) {
         QD_CUDA(cudaFuncSetAttribute(fk_tcfir<8, 13>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

@@ -164,6 +164,7 @@ def test_full_size_config2_checks(Q):
     assert ln == 1 + (n - 40) // 8
     chunks = -(-ln // 0x1000)
     d_out = torch.zeros(2 * chunks * 0x1000, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own (non-blocking) stream
     # one read more than there are chunks: the reference's loop makes it too, gets 0 samples and panics
     got_n, rc = chain.write_into(0x1000, 0, chunks + 1, d_out.data_ptr(), chunks * 0x1000, Q._lib.SPACE_DEVICE)
     chain.synchronize()
@@ -179,6 +180,7 @@ def test_full_size_config2_checks(Q):
         assert_bit_equal(got, want, f"chunk {c}")
     # two shards reproduce every output sample of the unsharded run
     d_out2 = torch.zeros_like(d_out)
+    torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own (non-blocking) stream
     for r in range(2):
         p = Q.shard_plan(fmt, rate, n, st, Q.shard.SINK_WRITE, 0x1000, 0x1000, 2, r)
         view = d_in[2 * p.first_sample : 2 * (p.first_sample + p.n_samples)]
@@ -212,6 +214,7 @@ def test_full_size_config4_shape_sampled_rows(Q):
     first = -(-base // (128 * 16))
     n_rows = rows_total - first
     d_idx = torch.zeros(n_rows * 128, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own (non-blocking) stream
     assert chain.spark_fft_device(128, 128, (0.5, 50.0), first, n_rows, d_idx.data_ptr()) == n_rows
     chain.synchronize()
     idx = d_idx.cpu().numpy().reshape(n_rows, 128)
@@ -409,6 +412,7 @@ def test_fast_mode_full_size_config2_against_exact(Q):
         chain = Q.Samples.from_device(d_in.data_ptr(), 2 * n, fmt, rate, keep=(d_in,)).shift(1_500_000)
         chain = chain.lowpass(1_000_000, 8, 40).with_precision(prec)
         d_out = torch.zeros(2 * chunks * 0x1000, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own (non-blocking) stream
         got_n, rc = chain.write_into(0x1000, 0, chunks, d_out.data_ptr(), chunks * 0x1000, Q._lib.SPACE_DEVICE)
         chain.synchronize()
         assert got_n == chunks * 0x1000 and rc == 0
@@ -442,6 +446,7 @@ def test_shards_and_pointers_at_awkward_alignments(Q):
         # the same bytes at an odd device address: the fused kernel's bulk copies need absolute sample 0 on a
         # 16-byte boundary, so this goes through the general executor
         buf = torch.zeros(part.size + 64, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own (non-blocking) stream
         off = 2 + 2 * (base % 7)  # sample-aligned, not 16-byte aligned
         buf[off : off + part.size] = torch.from_numpy(part).cuda()
         d = Q.Samples.from_device(buf.data_ptr() + off, part.size, Q.CS8, 20_000_000, base_sample=base, total_samples=n,
@@ -548,12 +553,14 @@ def test_fast_full_size_config2_shards_and_host_path_bitwise(Q):
 
     chunks = 32767
     d_out = torch.zeros(2 * chunks * 0x1000, dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own (non-blocking) stream
     whole = build(Q.Samples.from_device(d_in.data_ptr(), 2 * n, fmt, rate, keep=(d_in,)))
     got_n, _ = whole.write_into(0x1000, 0, chunks, d_out.data_ptr(), chunks * 0x1000, Q._lib.SPACE_DEVICE)
     whole.synchronize()
     assert got_n == chunks * 0x1000
     for n_shards in (2, 3):
         d_out2 = torch.zeros_like(d_out)
+        torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own (non-blocking) stream
         for r in range(n_shards):
             p = Q.shard_plan(fmt, rate, n, st, Q.shard.SINK_WRITE, 0x1000, 0x1000, n_shards, r)
             view = d_in[2 * p.first_sample : 2 * (p.first_sample + p.n_samples)]
@@ -596,6 +603,7 @@ def _full_size_sparkfft(Q, fmt, rate, total, stages, W, S, rng, synth_args, need
     whole = build(Q.Samples.from_device(d_in.data_ptr(), pb * total, fmt, rate, keep=(d_in,)))
     rows_total = whole.spark_rows(W, S)
     d_idx = torch.zeros(rows_total * W, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own
     assert whole.spark_fft_device(W, S, rng, 0, rows_total, d_idx.data_ptr()) == rows_total
     whole.synchronize()
     rows = [r if r >= 0 else rows_total + r for r in sample_rows]
@@ -605,6 +613,7 @@ def _full_size_sparkfft(Q, fmt, rate, total, stages, W, S, rng, synth_args, need
         assert np.array_equal(got, widx), f"row {r}"
     assert int(d_idx.max()) <= 8 and int((d_idx > 0).sum()) > 0
     d_idx2 = torch.zeros_like(d_idx)
+    torch.cuda.synchronize()
     for r in range(2):
         p = Q.shard_plan(fmt, rate, total, stages, Q.shard.SINK_SPARKFFT, W, S, 2, r)
         view = d_in[pb * p.first_sample : pb * (p.first_sample + p.n_samples)]

@@ -375,6 +375,7 @@ def test_device_resident_source_and_device_outputs(Q):
     g = Q.Samples.from_device(d_raw.data_ptr(), raw.size, Q.CS8, 20_000_000, keep=(d_raw,))
     g = g.shift(1_500_000).lowpass(1_000_000, 8, 40)
     out = torch.zeros(2 * (n // 8 + 8), dtype=torch.float32, device="cuda")
+    torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own (non-blocking) stream
     got_n, rc = g.write_into(0x1000, 0, 10**6, out.data_ptr(), out.numel() // 2, Q._lib.SPACE_DEVICE)
     g.synchronize()
     with kept_only():
@@ -383,6 +384,7 @@ def test_device_resident_source_and_device_outputs(Q):
     assert_bit_equal(out.cpu().numpy()[: 2 * got_n].view(np.complex64), want, "device write")
     rows = g.spark_rows(64, 64)
     d_idx = torch.zeros(rows * 64, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own (non-blocking) stream
     assert g.spark_fft_device(64, 64, (0.05, 2.0), 0, rows, d_idx.data_ptr()) == rows
     g.synchronize()
     with kept_only():

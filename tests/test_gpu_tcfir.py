@@ -74,10 +74,11 @@ def test_tensor_core_fir_within_1e5_of_the_oracle(Q, rate, stages, base, chunk):
 
 
 def test_shapes_the_tensor_core_kernel_declines_run_on_the_cuda_cores(Q):
-    """decimate 2 (176 accumulator columns, exchange buffers beyond shared memory), n * ratio >= 2^29 (the reference's
-    phase rounding, which only the CUDA-core kernel re-applies, would show) and windows that are not back to back."""
+    """A long filter whose exchange buffers exceed shared memory, and n * ratio >= 2^29 (the reference's phase rounding,
+    which only the CUDA-core kernel re-applies, would show)."""
     rate = 20_000_000
-    for stages, base in (([("shift", 1_000_000), ("lowpass", 4_000_000, 2, 18)], 0),
+    for stages, base in (([("shift", 1_000_000), ("lowpass", 1_000_000, 8, 400)], 0),
+                         ([("shift", 1_000_000), ("lowpass", 4_000_000, 2, 18)], 0),
                          ([("shift", 9_999_999), ("lowpass", 1_000_000, 8, 40)], 2**30 // (8 * 0x1000) * 8 * 0x1000)):
         D = _mult(stages)
         n = 0x1000 * D * 4 + 5000
@@ -146,6 +147,7 @@ def test_device_resident_capture_and_output(Q):
         chain = Q.Samples.from_device(d_in.data_ptr(), 2 * n, Q.CS8, rate, keep=(d_in,)).shift(1_500_000).lowpass(1_000_000, 8, 40)
         chain = chain.with_precision(prec).set_option("use_tc", tc)
         d_out = torch.zeros(2 * chunks * chunk, dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()  # the fill runs on torch's stream, the chain on its own (non-blocking) stream
         got_n, rc = chain.write_into(chunk, 0, chunks, d_out.data_ptr(), chunks * chunk, Q._lib.SPACE_DEVICE)
         chain.synchronize()
         assert got_n == chunks * chunk and rc == 0
