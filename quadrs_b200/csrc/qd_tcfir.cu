@@ -16,10 +16,10 @@
 // row phasor (one f64 sin/cos per row, from the table the exact mixer uses) and sums the 1 + (NOUT-1)/OPR rows that
 // meet in an output, in ascending row order.
 //
-// Roles (one persistent CTA per SM, 26 warps): warps 0-7 epilogue (two groups of four taking alternate tiles, TMEM
+// Roles (one persistent CTA per SM, 19 warps): warps 0-7 epilogue (two groups of four taking alternate tiles, TMEM
 // lane quarter = warp & 3); warp 8 TMEM allocation + the single MMA-issuing thread; warp 9 one thread issuing 16 KB
 // bulk copies (TMA) of the tiles' raw bytes into a ring of up to 8 slots (~100 KB of loads in flight per SM); warp 10
-// the tiles' f64 phase anchors; warps 11-26 converters: raw bytes from the ring, int8 -> f16 by PRMT into the mantissa of 1024 (no
+// the tiles' f64 phase anchors; warps 11-18 converters: raw bytes from the ring, int8 -> f16 by PRMT into the mantissa of 1024 (no
 // I2F), 128B-swizzled K-major stores, fence.proxy.async, mbarrier arrive.
 #include <cuda_fp16.h>
 
@@ -36,7 +36,7 @@ namespace qd {
 constexpr int kTcRows = 128;           // rows (of 64 samples) per MMA tile = UMMA M
 constexpr int kTcRowSamples = 64;      // K = 128 reals = two 128-byte swizzle atoms of f16
 constexpr int kTcEpiWarps = 8;           // two groups of four (TMEM lane quarter = warp & 3) taking alternate tiles
-constexpr int kTcProdWarps = 16;
+constexpr int kTcProdWarps = 8;
 constexpr int kTcThreads = 32 * (kTcEpiWarps + 3 + kTcProdWarps);
 constexpr uint32_t kTcStageBytes = 2 * kTcRows * 128; // one tile of A: two K atoms of 128 rows x 128 bytes
 constexpr uint32_t kTcStages = 2;
@@ -471,9 +471,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
 #pragma unroll
                 for (int i = 0; i < kPer; i++) v[i] = tc_load_chunk(a, n0 + (g_off[i] >> 1));
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&hd->raw_empty[slot]); // the slot's bytes are in registers: it may be refilled
-            if (++slot == a.raw_slots) slot = 0, rph ^= 1;
             mbar_wait_tc(&hd->empty[st], ph ^ 1);
             const uint32_t stage = sA_u32 + st * kTcStageBytes;
 #pragma unroll
@@ -488,7 +485,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
             }
             fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
             __syncwarp();
-            if (lane == 0) mbar_arrive(&hd->full[st]);
+            if (lane == 0) {
+                mbar_arrive(&hd->full[st]);
+                mbar_arrive(&hd->raw_empty[slot]); // the slot's bytes have been read and used: it may be refilled
+            }
+            if (++slot == a.raw_slots) slot = 0, rph ^= 1;
         }
     }
 
