@@ -146,6 +146,7 @@ struct TcHeader {
     double2 w[kTcRows];            // e^{i ratio 64 r}, r < 128
 };
 static_assert(sizeof(TcHeader) <= 4096, "header region");
+static_assert(kTcStages == 2, "a converter group owns one stage");
 
 // four int8 I/Q bytes (two complex samples) -> two half2 (re, im): byte + 128 dropped into the mantissa of 1024.0h is
 // the half 1024 + 128 + x; one exact packed subtraction leaves x
@@ -207,12 +208,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
     // ---- setup: barriers, TMEM, the B image
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < kTcStages; s++) {
-            mbar_init(&hd->full[s], kTcProdWarps);
+            mbar_init(&hd->full[s], kTcProdWarps / 2);
             mbar_init(&hd->empty[s], 1);
         }
         for (uint32_t s = 0; s < kTcRawMax; s++) {
             mbar_init(&hd->raw_full[s], 1);
-            mbar_init(&hd->raw_empty[s], kTcProdWarps);
+            mbar_init(&hd->raw_empty[s], kTcProdWarps / 2);
         }
         for (uint32_t s = 0; s < kTcAnchors; s++) {
             mbar_init(&hd->anc_full[s], 1);
@@ -278,7 +279,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
             mbar_wait_tc(&hd->acc_full[acc], aph);
             tc_fence_after();
             if constexpr (FIXED) {
-                constexpr int NC = 2 * NOUT_, NH = (2 * NOUT_ + 7) / 8 * 8, XPF = 2 * (NOUT_ - OPR_) + 2;
+                constexpr int NC = 2 * NOUT_, NH = (2 * NOUT_ + 7) / 8 * 8, XPF = 2 * ((NOUT_ - OPR_) | 1); // 64-bit accesses at a pitch of 2 * odd words: no bank conflicts
                 float part[NC];
                 if constexpr (NH % 16 == 0) {
 #pragma unroll
@@ -438,23 +439,25 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
             if (valid && (lane & 1) == 0) mbar_arrive(&hd->anc_full[k % kTcAnchors]);
         }
     } else {
-        // ================= converters: raw bytes -> f16 A tile (K-major, 128-byte swizzle)
-        constexpr int kPer = kTcRows * 8 / (32 * kTcProdWarps); // 16-byte chunks per thread and tile
-        const int pw = warp - kTcEpiWarps - 3;
-        const uint32_t row4 = 2 * (lane >> 4) + ((lane >> 2) & 1), ka = (lane >> 3) & 1, cp = lane & 3;
-        // per-thread constants: byte offset of its chunks inside a tile's raw bytes, and where their two 16-byte f16
-        // halves go inside a stage
-        uint32_t g_off[kPer], s_off[kPer][2];
-#pragma unroll
-        for (int i = 0; i < kPer; i++) {
-            const uint32_t row = 4 * (i * kTcProdWarps + pw) + row4;
-            g_off[i] = row * 128 + 16 * (ka * 4 + cp);
-            s_off[i][0] = ka * (kTcRows * 128) + row * 128 + (((2 * cp) ^ (row & 7)) << 4);
-            s_off[i][1] = ka * (kTcRows * 128) + row * 128 + (((2 * cp + 1) ^ (row & 7)) << 4);
-        }
+        // ================= converters: raw bytes -> f16 A tile (K-major, 128-byte swizzle); two groups of four warps
+        // take alternate tiles (group = stage = k & 1), so two tiles are being converted at any time
+        constexpr int kGroupWarps = kTcProdWarps / 2;
+        constexpr int kPer = kTcRows * 8 / (32 * kGroupWarps); // 16-byte chunks per thread and tile
+        const int cw = warp - kTcEpiWarps - 3, cg = cw / kGroupWarps, pw = cw % kGroupWarps;
+        // A quarter warp (one 128-byte shared-memory wavefront) takes the first half of a row's raw bytes and the second
+        // half of the next row's: 128 distinct bytes on the read side, and on the write side eight distinct 16-byte
+        // columns of the swizzled layout (row parity flips the column parity).
+        const uint32_t sub = (lane >> 2) & 1, row4 = 2 * (lane >> 4) + sub, ka = ((lane >> 3) & 1) ^ sub, cp = lane & 3;
+        // chunk i of the thread: row = 4 * (i * kGroupWarps + pw) + row4, i.e. 16 * kGroupWarps / 4 rows further per i
+        const uint32_t row_0 = 4 * pw + row4;
+        constexpr uint32_t kStep = 4 * kGroupWarps * 128; // bytes from chunk i to chunk i + 1, raw and converted alike
+        static_assert((4 * kGroupWarps) % 8 == 0, "the swizzle phase (row & 7) must not depend on i");
+        const uint32_t g_off0 = row_0 * 128 + 16 * (ka * 4 + cp);
+        const uint32_t s_off0 = ka * (kTcRows * 128) + row_0 * 128 + (((2 * cp) ^ (row_0 & 7)) << 4);
+        const uint32_t s_off1 = ka * (kTcRows * 128) + row_0 * 128 + (((2 * cp + 1) ^ (row_0 & 7)) << 4);
         const uint32_t sA_u32 = smem_u32(sA), raw_u32 = smem_u32(smem + a.off_raw);
-        uint32_t slot = 0, rph = 0;
-        for (uint32_t k = 0; k < n_my; k++) {
+        uint32_t slot = cg % a.raw_slots, rph = 0;
+        for (uint32_t k = cg; k < n_my; k += 2) {
             const uint32_t st = k % kTcStages, ph = (k / kTcStages) & 1;
             uint4 v[kPer];
             const int64_t n0 = (a.row_first + static_cast<int64_t>(blockIdx.x + k * gridDim.x) * a.rows_eff) * kTcRowSamples;
@@ -465,11 +468,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                 for (int i = 0; i < kPer; i++)
                     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                                  : "=r"(v[i].x), "=r"(v[i].y), "=r"(v[i].z), "=r"(v[i].w)
-                                 : "r"(raw_u32 + slot * kTcRawBytes + g_off[i])
+                                 : "r"(raw_u32 + slot * kTcRawBytes + g_off0 + i * kStep)
                                  : "memory");
             } else {
 #pragma unroll
-                for (int i = 0; i < kPer; i++) v[i] = tc_load_chunk(a, n0 + (g_off[i] >> 1));
+                for (int i = 0; i < kPer; i++) v[i] = tc_load_chunk(a, n0 + ((g_off0 + i * kStep) >> 1));
             }
             mbar_wait_tc(&hd->empty[st], ph ^ 1);
             const uint32_t stage = sA_u32 + st * kTcStageBytes;
@@ -480,8 +483,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                 cvt_s8x4(v[i].y, lo4.z, lo4.w);
                 cvt_s8x4(v[i].z, hi4.x, hi4.y);
                 cvt_s8x4(v[i].w, hi4.z, hi4.w);
-                sts_v4(stage + s_off[i][0], lo4);
-                sts_v4(stage + s_off[i][1], hi4);
+                sts_v4(stage + s_off0 + i * kStep, lo4);
+                sts_v4(stage + s_off1 + i * kStep, hi4);
             }
             fence_proxy_async(); // generic-proxy stores -> visible to the tensor core's async-proxy reads
             __syncwarp();
@@ -489,7 +492,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) fk_tcfir(const __grid_constant_
                 mbar_arrive(&hd->full[st]);
                 mbar_arrive(&hd->raw_empty[slot]); // the slot's bytes have been read and used: it may be refilled
             }
-            if (++slot == a.raw_slots) slot = 0, rph ^= 1;
+            slot += 2; // the group's next tile is two tiles on
+            if (slot >= a.raw_slots) slot -= a.raw_slots, rph ^= 1;
         }
     }
 
@@ -524,7 +528,7 @@ bool tcfir_geometry(uint32_t L, uint32_t D, TcGeom *g)
     g->XP = (2 * g->NOUT) | 1;
     // B image + exchange buffers + the A stages must fit one CTA's shared memory (tcfir_smem_layout)
     const bool fixed = g->OPR == 8 && g->NOUT == 13;
-    const uint32_t x_bytes = fixed ? 4 * kTcRows * (2 * (g->NOUT - g->OPR) + 2) * 4 : 2 * kTcRows * g->XP * 4;
+    const uint32_t x_bytes = fixed ? 4 * kTcRows * (2 * ((g->NOUT - g->OPR) | 1)) * 4 : 2 * kTcRows * g->XP * 4;
     const uint32_t off_a = (4096 + 2 * g->N * 128 + x_bytes + 1023) / 1024 * 1024;
     if (off_a + kTcStages * kTcStageBytes + 2 * kTcRawBytes > 227 * 1024 - 1024) return false;
     return true;
@@ -603,7 +607,7 @@ int launch_tcfir(Chain &c, const TcGeom &g, const uint8_t *d_bimg, float s_hi, f
     a.off_b = 4096;
     a.off_x = a.off_b + 2 * g.N * 128;
     const bool fixed = g.OPR == 8 && g.NOUT == 13; // the reference's default filter (40 taps) at decimate 8: config 2
-    const uint32_t x_bytes = fixed ? 4 * kTcRows * (2 * (g.NOUT - g.OPR) + 2) * 4 : 2 * kTcRows * g.XP * 4;
+    const uint32_t x_bytes = fixed ? 4 * kTcRows * (2 * ((g.NOUT - g.OPR) | 1)) * 4 : 2 * kTcRows * g.XP * 4;
     a.off_a = (a.off_x + x_bytes + 1023) / 1024 * 1024;
     const uint32_t cap = 227 * 1024 - 1024;
     a.off_raw = a.off_a + kTcStages * kTcStageBytes;
