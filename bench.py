@@ -555,6 +555,20 @@ def run_workload(cx, name, w, headline):
             "kernel_frac": (alg_bytes / (kern_ms * 1e-3) / 1e9 / peak) if kern_ms > 0 else None,
             "step_ms": ms_dev, "algorithmic_bytes_per_step": alg_bytes, "peak_source": peak_src,
             "hbm_ceiling_msamples_per_s": hbm_ceiling}
+    if "fk_tcfir" in (kern_name or ""):
+        # the filter ran on the tensor cores: per 64-sample row one 128 (K) x N (columns) slice of a tcgen05.mma tile, N =
+        # 2 tap halves x (re, im) x the outputs a row takes part in, padded to 8 columns per half
+        lp = [st for st in w["stages"] if st[0] == "lowpass"][0]
+        D, L = lp[2], lp[3]
+        nout = (63 - (L - L // 2)) // D + ((L - L // 2) + L - 1) // D + 1
+        n_cols = 2 * ((2 * nout + 7) // 8 * 8)
+        flop = 2.0 * 128 * n_cols / 64
+        tp, tp_src = getattr(cx, "tensor_peak", (None, None))
+        ach = value / world * 1e6 * flop / 1e12
+        roof["tensor_cobound"] = {"flop_per_sample": flop, "mma_n": n_cols, "achieved_tflops": ach, "peak_tflops": tp,
+                                  "peak_source": tp_src, "frac": (ach / tp) if tp else None,
+                                  "note": "f16 x f16 -> f32 tcgen05.mma; the HBM roofline binds, not the tensor cores"}
+        cob = None  # the packed-FP32 floor describes the CUDA-core filter
     if cob:
         per_gpu = value / world
         cob["min_hbm_fp32_ceiling_msamples_per_s"] = min(hbm_ceiling, cob["ceiling_msamples_per_s"])
@@ -762,6 +776,7 @@ def run_b200(args):
     peaks_path = ROOT / "MEASURED_PEAKS.json"
     if peaks_path.exists():
         cx.peak = (json.loads(peaks_path.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (of measured)")
+        cx.tensor_peak = (json.loads(peaks_path.read_text()).get("bf16_tflops_sustained"), "MEASURED_PEAKS.json bf16_tflops_sustained")
     else:
         cx.peak = (6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)")
     tpath = ROOT / "profiles" / "traffic.json"

@@ -144,7 +144,8 @@ int qd_chain_set_precision(qd_chain *c, int precision);
 int qd_chain_synchronize(qd_chain *c);
 /* Tuning knobs (tests and benches): "use_fast" 0/1 (0 forces the general unit-local executor), "fuse_stft" 0/1/2 (sparkfft inside the
  * filter kernel: never / back-to-back windows / also overlapping windows and two-stage chains),
- * "segment_bytes" raw bytes staged per pipelined segment for host/file sources,
+ * "use_tc" 0/1 (FAST precision over cs8 captures: 1, the default, runs the filter on the tensor cores where the chain's shape allows;
+ * 0 keeps the CUDA-core kernel), "segment_bytes" raw bytes staged per pipelined segment for host/file sources,
  * "scratch_budget" bytes of device scratch the general executor may use per batch. */
 int qd_chain_set_option(qd_chain *c, const char *key, int64_t value);
 

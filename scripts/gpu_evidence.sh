@@ -19,7 +19,7 @@ for item in cfg4:268435456:exact cfg1:67108864:exact cfg2:268435456:fast cfg2:26
   K=2; [ $wl = cfg4 ] && K=1; [ $wl = cfg3 ] && K=1; [ $wl = cfg2 ] && K=1; [ $wl = cfg5 ] && K=3
   SK=$((2*K)); [ $wl = cfg5 ] && SK=24
   python bench.py $A > /dev/null 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:'fk_fir|fk_tail|fk_stft' -s $SK -c $K -f -o $O/${TAG}_full_${wl}_$P python bench.py $A > $O/${TAG}_ncuf_${wl}_$P.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:'fk_fir|fk_tcfir|fk_tail|fk_stft' -s $SK -c $K -f -o $O/${TAG}_full_${wl}_$P python bench.py $A > $O/${TAG}_ncuf_${wl}_$P.log 2>&1
   python scripts/ncu_summary.py $O/${TAG}_full_${wl}_$P.ncu-rep --stalls --hot --title "ncu --set full --clock-control none --import-source on: python bench.py $A" > $O/${TAG}_full_${wl}_${P}_summary.txt 2>&1
   rm -f $O/${TAG}_full_${wl}_$P.ncu-rep
 done

@@ -77,3 +77,17 @@ def test_bulk_copy_and_packed_fp32_are_in_the_shipped_kernels(built):
     text = subprocess.run(["cuobjdump", "-sass", str(built / "qd_fast_d8.o")], capture_output=True, text=True, check=True).stdout
     for mnemonic in ("UBLKCP", "SYNCS", "FFMA2", "FMUL2"):
         assert mnemonic in text, mnemonic
+
+
+def test_tensor_core_fir_uses_tcgen05_tmem_and_the_bulk_copy_engine(built):
+    """fk_tcfir (qd_tcfir.cu): UTCHMMA = tcgen05.mma kind::f16, LDTM = tcgen05.ld (accumulators read back from TMEM),
+    UTCBAR = tcgen05.commit onto an mbarrier, UBLKCP = the 16 KB bulk copies of raw bytes; and no I2F in the int8 -> f16
+    conversion (PRMT into the mantissa of 1024.0h, one packed subtraction: no I2F to f16)."""
+    for name, addr, ins in functions(built / "qd_tcfir.o"):
+        if "fk_tcfir" not in name:
+            continue
+        text = "\n".join(ins)
+        for mnemonic in ("UTCHMMA", "LDTM", "UTCBAR", "UBLKCP", "SYNCS", "PRMT", "HADD2"):
+            assert mnemonic in text, (name, mnemonic)
+        assert sum(x.startswith("UTCHMMA") or " UTCHMMA" in x for x in ins) >= 8, name  # K = 128 as eight K = 16 steps
+        assert not any(re.search(r"I2F(P)?\.F16", x) for x in ins), name  # int8 -> f16 without conversion instructions
