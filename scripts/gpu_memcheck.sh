@@ -11,6 +11,7 @@ timeout 1100 compute-sanitizer --tool memcheck --error-exitcode 99 --print-limit
   "tests/test_gpu_multi.py" \
   "tests/test_gpu_parity.py::test_read_at_bit_exact_including_truncated_tail" \
   "tests/test_gpu_parity.py::test_sparkfft_bucket_indices_bit_exact" \
+  "tests/test_gpu_tcfir.py" \
   > gpurun_out/r2_memcheck.log 2>&1
 echo "exit $?" >> gpurun_out/r2_memcheck.log
 tail -15 gpurun_out/r2_memcheck.log
