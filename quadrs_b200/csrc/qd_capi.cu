@@ -316,6 +316,8 @@ int qd_chain_set_option(qd_chain *c, const char *key, int64_t value)
     if (!strcmp(key, "use_fast")) c->use_fast = value != 0;
     else if (!strcmp(key, "fuse_stft") && value >= 0 && value <= 2) c->fuse_stft = static_cast<int>(value);
     else if (!strcmp(key, "use_tc") && value >= 0 && value <= 1) c->use_tc = static_cast<int>(value);
+    else if (!strcmp(key, "glyph_lin") && value >= 0 && value <= 1) c->glyph_lin = static_cast<int>(value);
+    else if (!strcmp(key, "stft_minb") && value >= 2 && value <= 4) c->stft_minb = static_cast<int>(value);
     else if (!strcmp(key, "fir_cta_cap") && value >= 0) c->fir_cta_cap = static_cast<int>(value);
     else if (!strcmp(key, "segment_bytes") && value > 0) c->segment_bytes = static_cast<size_t>(value);
     else if (!strcmp(key, "scratch_budget") && value > 0) c->scratch_budget = static_cast<size_t>(value);

@@ -1153,12 +1153,8 @@ __device__ __forceinline__ void fused_stft(const FirArgs &a, const TileGeo &g, f
     uint8_t *row = a.fft.idx + u * W + ((pos0 + W / 2) & (W - 1));
     if ((R == 4 || R == 8) && W >= 2 * R && !a.fft.mag && a.fft.use_thr && (reinterpret_cast<uintptr_t>(row) & 3) == 0) {
 #pragma unroll
-        for (int h = 0; h < R; h += 4) {
-            uint32_t word = 0;
-#pragma unroll
-            for (int r = 0; r < 4; r++) word |= static_cast<uint32_t>(glyph_fast(a.fft, Y[i0 + h + r])) << (8 * r);
-            *reinterpret_cast<uint32_t *>(row + h) = word;
-        }
+        for (int h = 0; h < R; h += 4)
+            *reinterpret_cast<uint32_t *>(row + h) = glyph4_word(a.fft, Y[i0 + h], Y[i0 + h + 1], Y[i0 + h + 2], Y[i0 + h + 3]);
     } else {
 #pragma unroll
         for (int r = 0; r < R; r++) {
@@ -1296,10 +1292,8 @@ __device__ __forceinline__ void fused_stream_stft(const FirArgs &a, const TileGe
         if (words) {
             for (uint32_t i = 4 * tid; i < nwin * W; i += 4 * NT) {
                 const uint32_t w = i >> logw, pos = i & (W - 1);
-                uint32_t word = 0;
-#pragma unroll
-                for (int r = 0; r < 4; r++) word |= static_cast<uint32_t>(glyph_fast(a.fft, Wk[i + r])) << (8 * r);
-                *reinterpret_cast<uint32_t *>(a.fft.idx + static_cast<uint64_t>(u_lo + w) * W + ((pos + W / 2) & (W - 1))) = word;
+                *reinterpret_cast<uint32_t *>(a.fft.idx + static_cast<uint64_t>(u_lo + w) * W + ((pos + W / 2) & (W - 1))) =
+                    glyph4_word(a.fft, Wk[i], Wk[i + 1], Wk[i + 2], Wk[i + 3]);
             }
         } else {
             for (uint32_t i = tid; i < nwin * W; i += NT) emit_bin(a.fft, static_cast<uint64_t>(u_lo + (i >> logw)), W, i & (W - 1), Wk[i]);

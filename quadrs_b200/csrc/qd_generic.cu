@@ -527,10 +527,11 @@ static int stage_source(Chain &c, uint64_t lo, uint64_t hi, GPlan *p)
 static int ensure_twiddles(Chain &c, size_t W)
 {
     if (c.twiddles_n == W) return QD_OK;
-    std::vector<float> tw(2 * W);
+    std::vector<float> tw(4 * W, 0.0f); // w(W, .), then the same values in fk_stft's thread order
     fft_twiddles(W, tw.data());
-    QD_TRY(c.ensure(c.twiddles, 2 * W * sizeof(float)));
-    QD_CUDA(cudaMemcpyAsync(c.twiddles.p, tw.data(), 2 * W * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+    c.twiddles_packed = stft_thread_twiddles(W, tw.data(), tw.data() + 2 * W) != 0;
+    QD_TRY(c.ensure(c.twiddles, 4 * W * sizeof(float)));
+    QD_CUDA(cudaMemcpyAsync(c.twiddles.p, tw.data(), 4 * W * sizeof(float), cudaMemcpyHostToDevice, c.stream));
     QD_CUDA(cudaStreamSynchronize(c.stream)); // tw is a stack-lifetime host vector
     c.twiddles_n = W;
     return QD_OK;
@@ -562,6 +563,7 @@ void fill_fft_args(Chain &c, const SinkArgs &sink, size_t W, FftArgs *fa)
     memset(fa, 0, sizeof *fa);
     fa->in_pitch = W;
     fa->tw = static_cast<const float2 *>(c.twiddles.p);
+    fa->twp = c.twiddles_packed && c.twiddles_n == W ? fa->tw + W : nullptr;
     fa->window = sink.windowed ? static_cast<const float *>(c.window.p) : nullptr;
     fa->W = static_cast<uint32_t>(W);
     fa->epi = sink.kind == SINK_SPARK ? EPI_SPARK : sink.kind == SINK_LEVELS ? EPI_LEVELS : EPI_TAKE;
@@ -640,6 +642,7 @@ static int fast_sink_prepare(Chain &c, void *user, int j, uint64_t u0, uint64_t 
     }
     fa->n_units = nu;
     stft_finalize_args(*fa);
+    if (!c.glyph_lin) fa->use_lin = 0;
     return QD_OK;
 }
 

@@ -145,6 +145,7 @@ struct Chain {
     Buf sink_a, sink_b, offsets;
     Buf twiddles, window;
     size_t twiddles_n = 0, window_n = 0;
+    bool twiddles_packed = false; // the thread-ordered copy follows the natural table
     void *h_pinned = nullptr; // staging for FILE sources and small D2H
     size_t h_pinned_cap = 0;
     size_t scratch_budget = size_t(1) << 30;
@@ -157,6 +158,8 @@ struct Chain {
     // FAST arithmetic over cs8 captures: the filter runs on the tensor cores (fk_tcfir, qd_tcfir.cu) when the chain's
     // shape allows; 0 keeps the CUDA-core kernel
     int use_tc = 1;
+    int stft_minb = 4; // experiment: resident CTAs per SM fk_stft<12> is compiled for (4: 64 registers, 3: 80, 2: 128)
+    int glyph_lin = 1; // glyph indices through the linear form where it is proven (FftArgs::use_lin); 0 keeps the thresholds
     Buf tc_bimg;                  // B operand image of the current filter
     std::vector<uint8_t> tc_host; // its host copy (source of the upload)
     uint64_t tc_key[4] = {0, 0, 0, 0}; // (L, D, bits of the ratio sum, tap checksum) the image was built for
@@ -255,6 +258,7 @@ struct FftArgs {
     uint64_t raw_first;
     uint64_t n_units;
     const float2 *tw;     // w(W, j), j < W
+    const float2 *twp;    // nullable: the same values in the order fk_stft's threads use them (stft_thread_twiddles)
     const float *window;  // nullable (take_fft BlackmanHarris)
     uint32_t W;
     uint32_t team;        // threads cooperating on one window
@@ -268,6 +272,12 @@ struct FftArgs {
     int use_thr;
     double thr[9];
     uint32_t thr_hi[9];   // their high words: s >= thr decides on the high word alone unless the two are equal
+    // The same boundaries as one linear function of the square root, g = lin_a * sqrt(s) + lin_b (glyph = floor g
+    // clamped to 0..8): evaluated in f32 and trusted only where g is further than lin_eps from an integer, every
+    // other bin goes through the thresholds (stft_finalize_args proves the margin on the host, else use_lin = 0).
+    int use_lin;
+    float lin_a, lin_bh, lin_bl; // slope; lin_b - 0.5 + lin_eps and lin_b - 0.5 - lin_eps
+    float lin_lo, lin_hi;        // clamp of the square root: g stays inside [0.5, 8.5]
     float2 one;           // (1, 1), opaque to ptxas (see qd_stft.cu pmul_tw)
 };
 // thr[c], c = 0..6: smallest s = fl64(re^2 + im^2) whose glyph index is >= c + 1; thr[7]: start of the
@@ -275,6 +285,9 @@ struct FftArgs {
 bool spark_thresholds(float mn, float mx, double thr[9]);
 int launch_stft_fast(Chain &c, const FftArgs &fa, uint64_t units, bool *handled);
 void stft_finalize_args(FftArgs &fa);
+// fk_stft's 16-point passes: pass p (q = 2^first_bits * 16^p points combined so far) reads its 15 twiddles per
+// thread as out[15 * (sum of earlier q) + j * q + k]; returns the number of float2 written (<= W; 0: no such pass)
+size_t stft_thread_twiddles(size_t W, const float *tw_re_im, float *out_re_im);
 
 // ---------------------------------------------------------------- single-process multi-GPU (qd_multi.cu)
 // Runs fn(i, shard i) for every shard of a sharded chain, each on its own host thread bound to the CPUs local

@@ -14,6 +14,7 @@
 //   * the last pass feeds the epilogue from registers: fftshifted bin, glyph index by comparing
 //     fl64(re^2 + im^2) with per-glyph thresholds (no square root), magnitudes only when asked for.
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "qd_device_math.cuh"
@@ -25,6 +26,10 @@ namespace qd {
 constexpr int kStftThreads = 256;
 
 __host__ __device__ constexpr uint32_t pad_idx(uint32_t i) { return i + (i >> 4) + (i >> 8); }
+// pad_idx(base + q*i) = pad_idx(base) + pad_off(q, i) for every (base, q, i) the passes below use (a group's base
+// has no bits between q and 16q resp. 4q, so nothing carries into the padding terms; scripts/check_stft_pad.py
+// enumerates all of them): one padded base per thread and compile-time offsets instead of two shifts per access
+__host__ __device__ constexpr uint32_t pad_off(uint32_t q, uint32_t i) { return q * i + ((q * i) >> 4) + ((q * i) >> 8); }
 
 // base-4 digit reversal of x over nd digits
 __device__ __forceinline__ uint32_t digitrev4(uint32_t x, int nd)
@@ -75,12 +80,13 @@ __device__ __forceinline__ void load_group(const FftArgs &a, uint64_t u, uint32_
 
 
 // two radix-4 levels on 16 points held by one thread: element i sits at position k + q*i of its block;
-// level 1 has sub-size q (twiddle index k), level 2 sub-size 4q (twiddle index k + q*c)
-__device__ __forceinline__ void levels2(float2 (&e)[16], uint32_t k, uint32_t q, uint32_t W, const float2 *__restrict__ T, float2 one)
+// level 1 has sub-size q (twiddle index k), level 2 sub-size 4q (twiddle index k + q*c).  tw(j) is the thread's
+// j-th twiddle in order of use: j < 3: w(4q, (j+1) k); then w(16q, m (k + q c)) at j = 3 + 3c + (m-1).
+template <typename Tw>
+__device__ __forceinline__ void levels2(float2 (&e)[16], uint32_t k, uint32_t q, float2 one, Tw tw)
 {
     if (k != 0) {
-        const uint32_t sc = W / (4 * q);
-        const float2 w1 = __ldg(T + k * sc), w2 = __ldg(T + 2 * k * sc), w3 = __ldg(T + 3 * k * sc);
+        const float2 w1 = tw(0), w2 = tw(1), w3 = tw(2);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             e[4 * j + 1] = pmul_tw(e[4 * j + 1], w1, one);
@@ -90,17 +96,23 @@ __device__ __forceinline__ void levels2(float2 (&e)[16], uint32_t k, uint32_t q,
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) pradix4(e[4 * j], e[4 * j + 1], e[4 * j + 2], e[4 * j + 3]);
-    const uint32_t sc2 = W / (16 * q);
 #pragma unroll
     for (int c = 0; c < 4; c++) {
         const uint32_t kp = k + q * c;
         if (kp != 0) {
-            e[c + 4] = pmul_tw(e[c + 4], __ldg(T + kp * sc2), one);
-            e[c + 8] = pmul_tw(e[c + 8], __ldg(T + 2 * kp * sc2), one);
-            e[c + 12] = pmul_tw(e[c + 12], __ldg(T + 3 * kp * sc2), one);
+            e[c + 4] = pmul_tw(e[c + 4], tw(3 + 3 * c), one);
+            e[c + 8] = pmul_tw(e[c + 8], tw(4 + 3 * c), one);
+            e[c + 12] = pmul_tw(e[c + 12], tw(5 + 3 * c), one);
         }
         pradix4(e[c], e[c + 4], e[c + 8], e[c + 12]);
     }
+}
+// the j-th twiddle of levels2 out of the natural table T = w(W, .)
+__device__ __forceinline__ float2 tw_natural(const float2 *__restrict__ T, uint32_t W, uint32_t k, uint32_t q, int j)
+{
+    if (j < 3) return __ldg(T + (j + 1) * k * (W / (4 * q)));
+    const int c = (j - 3) / 3, m = (j - 3) % 3 + 1;
+    return __ldg(T + m * (k + q * c) * (W / (16 * q)));
 }
 
 // one radix-4 level on 4 points: element i at position k + q*i, sub-size q
@@ -141,28 +153,26 @@ __device__ __forceinline__ void emit_window(const FftArgs &a, uint64_t u, const 
         for (int i = 0; i < N; i++) emit_bin(a, u, N, i, e[i]);
         return;
     }
-    uint32_t w[N >= 4 ? N / 4 : 1];
-#pragma unroll
-    for (int j = 0; j < N / 4; j++) w[j] = 0;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-        const int b = (i + N / 2) & (N - 1);
-        w[b / 4] |= static_cast<uint32_t>(glyph_fast(a, e[i])) << (8 * (b & 3));
-    }
     uint32_t *o = reinterpret_cast<uint32_t *>(a.idx + static_cast<size_t>(u) * N);
 #pragma unroll
-    for (int j = 0; j < N / 4; j++) o[j] = w[j];
+    for (int j = 0; j < N / 4; j++) { // word j = display positions 4j .. 4j+3 = bins (4j + N/2 ..) mod N
+        const int i = (4 * j + N / 2) & (N - 1);
+        o[j] = glyph4_word(a, e[i], e[(i + 1) & (N - 1)], e[(i + 2) & (N - 1)], e[(i + 3) & (N - 1)]);
+    }
 }
 
-// 16 bins of a wider window: staged as bytes in the team's row of shared memory (gl), written out by
-// store_row once the whole row is there
-__device__ __forceinline__ void stage_bin(const FftArgs &a, uint8_t *gl, uint32_t W, uint32_t pos, float2 v)
+// four bins of a wider window (positions pos, pos + q, ...): staged as bytes in the team's row of shared memory
+// (gl), written out 16 bytes per thread once the whole row is there
+__device__ __forceinline__ void stage_bins4(const FftArgs &a, uint8_t *gl, uint32_t W, uint32_t pos, uint32_t q, const float2 *e)
 {
-    gl[(pos + W / 2) & (W - 1)] = static_cast<uint8_t>(glyph_fast(a, v));
+    uint32_t g[4];
+    glyph4(a, e[0], e[1], e[2], e[3], g);
+#pragma unroll
+    for (int r = 0; r < 4; r++) gl[(pos + q * r + W / 2) & (W - 1)] = static_cast<uint8_t>(g[r]);
 }
 
-template <int LOGW>
-__global__ void __launch_bounds__(kStftThreads, 4) fk_stft(const __grid_constant__ FftArgs a)
+template <int LOGW, int MINB = 4>
+__global__ void __launch_bounds__(kStftThreads, MINB) fk_stft(const __grid_constant__ FftArgs a)
 {
     constexpr uint32_t W = 1u << LOGW;
     constexpr int M = LOGW / 2;
@@ -199,9 +209,9 @@ __global__ void __launch_bounds__(kStftThreads, 4) fk_stft(const __grid_constant
                 if (REST == 0) {
                     emit_window<8>(a, u, e);
                 } else {
-                    const uint32_t g = digitrev4(t2, M - 1);
+                    float2 *xg = x + pad_idx(8 * digitrev4(t2, M - 1));
 #pragma unroll
-                    for (int i = 0; i < 8; i++) x[pad_idx(8 * g + i)] = e[i];
+                    for (int i = 0; i < 8; i++) xg[i] = e[i];
                 }
             }
         }
@@ -210,13 +220,13 @@ __global__ void __launch_bounds__(kStftThreads, 4) fk_stft(const __grid_constant
             float2 e[16];
             // sample i = r_{m-1} + 4*r_m of the stride-TW comb  ->  leaf offset r_m + 4*r_{m-1}
             load_group<16>(a, u, lt, TW, e, [](int i) { return (i >> 2) | ((i & 3) << 2); });
-            levels2(e, 0, 1, W, T, a.one);
+            levels2(e, 0, 1, a.one, [&](int j) { return tw_natural(T, W, 0, 1, j); });
             if constexpr (REST == 0) {
                 emit_window<16>(a, u, e);
             } else {
-                const uint32_t g = digitrev4(lt, M - 2);
+                float2 *xg = x + pad_idx(16 * digitrev4(lt, M - 2));
 #pragma unroll
-                for (int i = 0; i < 16; i++) x[pad_idx(16 * g + i)] = e[i];
+                for (int i = 0; i < 16; i++) xg[i] = e[i];
             }
         }
     } else if constexpr (LOGW == 2) {
@@ -245,23 +255,34 @@ __global__ void __launch_bounds__(kStftThreads, 4) fk_stft(const __grid_constant
         __syncthreads();
         const bool last = (pass == N16 - 1) && N4 == 0;
         if (active) {
-            const uint32_t k = lt & (q - 1), blk = lt / q; // one group of 16 per thread
+            // one group of 16 per thread.  With q = 16 the blocks run along the lanes and k along the half warps:
+            // a warp then needs 2 values of every twiddle instead of 16 (its 15 twiddle loads were 240 L1
+            // wavefronts per pass at W = 4096), and the padded pitch of a block (273 float2) keeps the
+            // shared-memory accesses free of bank conflicts; other q keep k along the lanes.
+            const uint32_t NBLK = TW / q; // blocks of 16q points
+            const bool across = (q == 16) && NBLK > 1;
+            const uint32_t k = across ? lt / NBLK : (lt & (q - 1)), blk = across ? lt % NBLK : lt / q;
             const uint32_t base = blk * 16 * q + k;
+            float2 *xb = x + pad_idx(base);
             float2 e[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) e[i] = x[pad_idx(base + q * i)];
-            levels2(e, k, q, W, T, a.one);
+            for (int i = 0; i < 16; i++) e[i] = xb[pad_off(q, i)];
+            // the thread's 15 twiddles in order of use, [j][k] (stft_thread_twiddles): neighbouring k are neighbouring
+            // words, so a load is 1-2 lines per warp instead of up to 24 out of the natural table
+            const float2 *__restrict__ P = a.twp + (q - (1u << FIRST_BITS)); // 15 * (sum of q over the earlier passes)
+            if (a.twp) levels2(e, k, q, a.one, [&](int j) { return __ldg(P + j * q + k); });
+            else levels2(e, k, q, a.one, [&](int j) { return tw_natural(T, W, k, q, j); });
             if (last) {
                 if (staged) {
 #pragma unroll
-                    for (int i = 0; i < 16; i++) stage_bin(a, gl, W, base + q * i, e[i]);
+                    for (int i = 0; i < 16; i += 4) stage_bins4(a, gl, W, base + q * i, q, e + i);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; i++) emit_bin(a, u, W, base + q * i, e[i]);
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; i++) x[pad_idx(base + q * i)] = e[i];
+                for (int i = 0; i < 16; i++) xb[pad_off(q, i)] = e[i];
             }
         }
         q *= 16;
@@ -274,13 +295,13 @@ __global__ void __launch_bounds__(kStftThreads, 4) fk_stft(const __grid_constant
                 const uint32_t gid = lt + z * TW;
                 const uint32_t k = gid & (q - 1), blk = gid / q;
                 const uint32_t base = blk * 4 * q + k;
+                const float2 *xb = x + pad_idx(base);
                 float2 e[4];
 #pragma unroll
-                for (int i = 0; i < 4; i++) e[i] = x[pad_idx(base + q * i)];
+                for (int i = 0; i < 4; i++) e[i] = xb[pad_off(q, i)];
                 levels1(e, k, q, W, T, a.one);
                 if (staged) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) stage_bin(a, gl, W, base + q * i, e[i]);
+                    stage_bins4(a, gl, W, base, q, e);
                 } else {
 #pragma unroll
                     for (int i = 0; i < 4; i++) emit_bin(a, u, W, base + q * i, e[i]);
@@ -304,7 +325,7 @@ __global__ void __launch_bounds__(kStftThreads, 4) fk_stft(const __grid_constant
     }
 }
 
-template <int LOGW>
+template <int LOGW, int MINB = 4>
 static int launch_stft_k(Chain &c, const FftArgs &fa, uint64_t units)
 {
     constexpr uint32_t W = 1u << LOGW;
@@ -313,12 +334,74 @@ static int launch_stft_k(Chain &c, const FftArgs &fa, uint64_t units)
     constexpr int FIRST_BITS = (LOGW & 1) ? (LOGW >= 3 ? 3 : 1) : (LOGW >= 4 ? 4 : LOGW);
     const size_t smem = LOGW == FIRST_BITS ? 0 : static_cast<size_t>((WPC * (pad_idx(W) + 1) + 1) & ~1u) * sizeof(float2) + static_cast<size_t>(WPC) * W;
     if (smem > 48 * 1024)
-        QD_CUDA(cudaFuncSetAttribute(fk_stft<LOGW>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        QD_CUDA(cudaFuncSetAttribute(fk_stft<LOGW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const uint64_t grid = (units + WPC - 1) / WPC;
     if (grid > 0x7fffffffull) return set_error(QD_E_INVALID_ARG, "too many windows in one launch");
-    fk_stft<LOGW><<<static_cast<unsigned>(grid), kStftThreads, smem, c.stream>>>(fa);
+    fk_stft<LOGW, MINB><<<static_cast<unsigned>(grid), kStftThreads, smem, c.stream>>>(fa);
     QD_LAUNCHED();
     return QD_OK;
+}
+
+size_t stft_thread_twiddles(size_t W, const float *tw, float *out)
+{
+    if (W < 128 || W > 4096 || (W & (W - 1))) return 0;
+    int logw = 0;
+    while ((size_t(1) << logw) < W) logw++;
+    const int first = (logw & 1) ? 3 : 4;
+    const int n16 = (logw - first) / 4;
+    size_t q = size_t(1) << first, n = 0;
+    for (int pass = 0; pass < n16; pass++, q *= 16) {
+        for (int j = 0; j < 15; j++)
+            for (size_t k = 0; k < q; k++) {
+                const size_t c = j < 3 ? 0 : (j - 3) / 3, m = j < 3 ? j + 1 : (j - 3) % 3 + 1;
+                const size_t idx = j < 3 ? m * k * (W / (4 * q)) : m * (k + q * c) * (W / (16 * q));
+                out[2 * (n + j * q + k)] = tw[2 * idx];
+                out[2 * (n + j * q + k) + 1] = tw[2 * idx + 1];
+            }
+        n += 15 * q;
+    }
+    return n;
+}
+
+// The linear form of the glyph boundaries (FftArgs::use_lin), accepted only when it provably agrees with the
+// thresholds outside its band.  With g^(s) = lin_a * sqrt(s) + lin_b in exact arithmetic on the ROUNDED f32
+// coefficients, every threshold must lie within eps/2 of its integer: g^(thr[c]) = c + 1 for c < 7, = 8 for the
+// panic zone and for max.  The kernel's f32 evaluation is off g^ by at most
+//   E = (9 + |b|) * 1.5 * 2^-23  (re^2 + im^2 in f32: 2^-23 relative, halved by the root; sqrt.approx: 2^-23)
+//     + 9 * 2^-24                (the rounding of the fused multiply-add; g <= 9 after the clamps)
+//     + a * 2^-63                (flushed denormals: |sqrt| error <= 2^-63)
+// < eps/4 with eps = (9 + |b|) * 2^-20, so a bin whose g is further than eps from every integer has floor(g) on
+// the same side of every threshold as s itself (g^ is increasing).  re^2 + im^2 overflowing to inf in f32 must
+// mean "above max": g^(2^127) >= 9.
+static void stft_linear_glyphs(FftArgs &fa)
+{
+    fa.use_lin = 0;
+    fa.lin_a = fa.lin_bh = fa.lin_bl = fa.lin_lo = fa.lin_hi = 0.0f;
+    if (!fa.use_thr) return;
+    const double dist = static_cast<double>(fa.distinction);
+    if (!(dist > 0.0) || !std::isfinite(dist)) return;
+    const float a = static_cast<float>(1.0 / dist);
+    const float b = static_cast<float>(1.0 - static_cast<double>(fa.mn) / dist);
+    if (!std::isfinite(a) || !std::isfinite(b) || !(a > 0.0f) || a > 1.0e9f || std::fabs(b) > 8192.0f) return;
+    const double A = a, B = b;
+    const double eps = (9.0 + std::fabs(B)) * std::ldexp(1.0, -20);
+    for (int c = 0; c < 9; c++) {
+        const double t = fa.thr[c];
+        if (!(t >= 0.0) || !std::isfinite(t)) return; // NaN: the boundary does not exist (max = inf, ...)
+        const double target = c < 7 ? c + 1 : 8;
+        const double g = A * std::sqrt(t) + B;
+        if (t == 0.0 ? g < target - eps / 2 : std::fabs(g - target) > eps / 2) return;
+    }
+    if (A * std::sqrt(std::ldexp(1.0, 127)) + B < 9.0) return;
+    const float lo = B < 0.5 ? static_cast<float>((0.5 - B) / A) : 0.0f;
+    const float hi = static_cast<float>((8.5 - B) / A);
+    if (!(hi > lo) || !std::isfinite(hi)) return;
+    fa.lin_a = a;
+    fa.lin_bh = static_cast<float>(B - 0.5 + eps);
+    fa.lin_bl = static_cast<float>(B - 0.5 - eps);
+    fa.lin_lo = lo;
+    fa.lin_hi = hi;
+    fa.use_lin = 1;
 }
 
 // the glyph boundaries as thresholds on re^2 + im^2 (see FftArgs::thr) and the opaque (1, 1)
@@ -331,6 +414,7 @@ void stft_finalize_args(FftArgs &fa)
         fa.thr_hi[i] = static_cast<uint32_t>(bits >> 32);
     }
     fa.one = make_float2(1.0f, 1.0f);
+    stft_linear_glyphs(fa);
 }
 
 int launch_stft_fast(Chain &c, const FftArgs &fa_in, uint64_t units, bool *handled)
@@ -340,6 +424,7 @@ int launch_stft_fast(Chain &c, const FftArgs &fa_in, uint64_t units, bool *handl
     FftArgs fa = fa_in;
     fa.n_units = units;
     stft_finalize_args(fa);
+    if (!c.glyph_lin) fa.use_lin = 0;
     int logw = 0;
     while ((1u << logw) < fa.W) logw++;
     *handled = true;
@@ -356,7 +441,7 @@ int launch_stft_fast(Chain &c, const FftArgs &fa_in, uint64_t units, bool *handl
     case 9: return launch_stft_k<9>(c, fa, units);
     case 10: return launch_stft_k<10>(c, fa, units);
     case 11: return launch_stft_k<11>(c, fa, units);
-    case 12: return launch_stft_k<12>(c, fa, units);
+    case 12: return c.stft_minb == 3 ? launch_stft_k<12, 3>(c, fa, units) : c.stft_minb == 2 ? launch_stft_k<12, 2>(c, fa, units) : launch_stft_k<12>(c, fa, units);
     }
     *handled = false;
     return QD_OK;

@@ -84,6 +84,71 @@ __device__ __forceinline__ int glyph_fast(const FftArgs &a, float2 v)
     return g;
 }
 
+// ---- four glyphs at once through the linear form (FftArgs::use_lin) ----
+// fft.rs:53-60 is glyph = clamp(floor((norm - min) / distinction + 1), 0, 8) up to its own f32 roundings, so
+// g = lin_a * sqrt(re^2 + im^2) + lin_b in f32 (error bound E, stft_finalize_args) decides every bin whose g is
+// further than lin_eps >= 4 E from an integer.  floor(g) without a conversion: (g - 0.5 + eps) and (g - 0.5 - eps)
+// are both added to 1.5 * 2^23, which rounds them to integers in the low mantissa bits; equal results = same
+// integer on both sides of the band = decided.  A NaN propagates through the clamps and compares unequal.
+// 8 instructions per bin (FMUL, FFMA, MUFU.SQRT, 2 FMNMX, FFMA2, FADD2, FSETP) against ~40 for the thresholds.
+__device__ __forceinline__ float min_nan(float a, float b)
+{
+    float r;
+    asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float max_nan(float a, float b)
+{
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// low byte of the result = glyph; undecided |= the bin needs the thresholds
+__device__ __forceinline__ uint32_t glyph_lin(const FftArgs &a, float2 v, bool &undecided)
+{
+    const float s = fmaf(v.y, v.y, v.x * v.x);
+    const float r = min_nan(max_nan(sqrt_approx(s), a.lin_lo), a.lin_hi);
+    const float2 hl = fma2(make_float2(r, r), make_float2(a.lin_a, a.lin_a), make_float2(a.lin_bh, a.lin_bl));
+    const float2 m = add2(hl, make_float2(12582912.0f, 12582912.0f));
+    undecided |= !(m.x == m.y);
+    return __float_as_uint(m.x);
+}
+// the rare group with an undecided bin (or no linear form): the thresholds, out of line; byte i = glyph of v_i
+static __device__ __noinline__ uint32_t glyph4_by_threshold(const FftArgs &a, float2 v0, float2 v1, float2 v2, float2 v3)
+{
+    return static_cast<uint32_t>(glyph_fast(a, v0)) | static_cast<uint32_t>(glyph_fast(a, v1)) << 8 |
+           static_cast<uint32_t>(glyph_fast(a, v2)) << 16 | static_cast<uint32_t>(glyph_fast(a, v3)) << 24;
+}
+// glyphs of four bins: the low byte of g[i]
+__device__ __forceinline__ void glyph4(const FftArgs &a, float2 v0, float2 v1, float2 v2, float2 v3, uint32_t (&g)[4])
+{
+    bool undecided = !a.use_lin;
+    g[0] = glyph_lin(a, v0, undecided);
+    g[1] = glyph_lin(a, v1, undecided);
+    g[2] = glyph_lin(a, v2, undecided);
+    g[3] = glyph_lin(a, v3, undecided);
+    if (undecided) {
+        const uint32_t w = glyph4_by_threshold(a, v0, v1, v2, v3);
+        g[0] = w;
+        g[1] = w >> 8;
+        g[2] = w >> 16;
+        g[3] = w >> 24;
+    }
+}
+// ... packed into one word, byte i = glyph of v_i
+__device__ __forceinline__ uint32_t glyph4_word(const FftArgs &a, float2 v0, float2 v1, float2 v2, float2 v3)
+{
+    uint32_t g[4];
+    glyph4(a, v0, v1, v2, v3, g);
+    return __byte_perm(__byte_perm(g[0], g[1], 0x0040), __byte_perm(g[2], g[3], 0x0040), 0x5410);
+}
+
 // glyph index (and optional magnitude) of one output bin, fft.rs:48-60: the general form
 __device__ __forceinline__ void emit_bin(const FftArgs &a, uint64_t u, uint32_t W, uint32_t pos, float2 v)
 {

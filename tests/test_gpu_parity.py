@@ -455,3 +455,71 @@ def test_stft_thresholds_on_special_values(Q):
         assert rc_o == rc_g, (rng_, rc_o, rc_g)
         if rc_o == 0:
             assert np.array_equal(idx, widx), rng_
+
+
+# ---------------------------------------------------------------- glyphs through the linear form (qd_stft_epilogue.cuh glyph4)
+LIN_RANGES = [(0.05, 2.0), (0.001, 0.01), (0.5, 50.0), (100.0, 100.5), (0.0, 1.0), (3.0, 4.0e6), (1e-20, 1e-18), (0.08, 1.0)]
+
+
+def _boundary_magnitudes(lo, hi, seed):
+    """f32 magnitudes on, next to and between the glyph boundaries of lo:hi (fft.rs:45-60)."""
+    lo32, hi32 = np.float32(lo), np.float32(hi)
+    d = np.float32((hi32 - lo32) / np.float32(7))
+    vals = []
+    for k in range(9):
+        e = np.float32(lo32 + np.float32(k) * d) if k < 8 else hi32
+        for near in (e, np.float32(float(e) * (1 - 3e-6)), np.float32(float(e) * (1 + 3e-6)), np.float32(float(e) * (1 - 4e-5)), np.float32(float(e) * (1 + 4e-5))):
+            v = np.float32(near)
+            run = [v]
+            up, dn = v, v
+            for _ in range(24):
+                up = np.nextafter(up, np.float32(np.inf))
+                dn = np.nextafter(dn, np.float32(0))
+                run += [up, dn]
+            vals += run
+    r = np.random.default_rng(seed)
+    vals += list(np.exp(r.uniform(np.log(max(lo, 1e-30) / 30), np.log(hi * 30), 600)).astype(np.float32))
+    vals += list(r.uniform(lo, hi, 600).astype(np.float32))
+    vals += [0.0, 1e-42, 1e-30, 1.9e19, 3e38, np.inf, np.nan]
+    return np.array(vals, dtype=np.float32)
+
+
+@pytest.mark.parametrize("rng_", LIN_RANGES)
+@pytest.mark.parametrize("W", [4, 16, 64, 256, 4096])
+def test_glyph_linear_form_agrees_on_and_around_every_boundary(Q, W, rng_):
+    """A window that is v at sample 0 and zero elsewhere transforms to v in every bin, exactly (only additions of
+    zeros), so the bins can be placed on, one ulp beside and a few 1e-6 beside every glyph boundary: the linear
+    form must hand exactly those to the thresholds and agree with the oracle everywhere else.  v is split over
+    re and im at several angles, so re^2 + im^2 rounds differently in f32 (kernel) and f64 (thresholds)."""
+    mags = _boundary_magnitudes(*rng_, seed=W)
+    if W == 4096:
+        mags = mags[:: 7]
+
+    def run(chain):
+        try:
+            return 0, chain.spark_fft(W, W, rng_)[0]
+        except (O.OracleError, Q.QdError) as e:
+            return e.code, None
+
+    # first with every magnitude (a range whose top boundary reaches graph[7] panics: same status), then without
+    # the few ulps below max where the reference panics
+    for keep_panic_zone in (True, False):
+        m = mags if keep_panic_zone else mags[~((mags > rng_[1] * (1 - 1e-5)) & (mags < rng_[1]))]
+        ang = np.random.default_rng(W + 1).choice([0.0, np.pi / 2, 0.3, 0.7853981, 1.2, 2.9], size=len(m))
+        sig = np.zeros((len(m), W), dtype=np.complex64)
+        with np.errstate(invalid="ignore", over="ignore"):
+            sig[:, 0] = (m * np.cos(ang)).astype(np.float32) + 1j * (m * np.sin(ang)).astype(np.float32)
+        sig[ang == 0.0, 0] = m[ang == 0.0]  # the magnitude itself, bit for bit
+        raw = sig.reshape(-1).view(np.uint8)
+        rc_o, widx = run(O.Samples.from_bytes(raw, O.CF32, 1000))
+        rc_g, idx = run(Q.Samples.from_bytes(raw, Q.CF32, 1000))
+        rc_t, tidx = run(Q.Samples.from_bytes(raw, Q.CF32, 1000).set_option("glyph_lin", 0))
+        assert rc_o == rc_g == rc_t, (keep_panic_zone, rc_o, rc_g, rc_t)
+        if rc_o == 0:
+            bad = np.argwhere(idx != widx)
+            assert len(bad) == 0, (rng_, W, len(bad), [(float(m[r]), int(idx[r, c]), int(widx[r, c])) for r, c in bad[:5]])
+            assert np.array_equal(tidx, widx)
+            assert len(np.unique(widx)) >= 5
+            break
+    else:
+        raise AssertionError(f"range {rng_} panics even without the zone below max")
