@@ -29,6 +29,19 @@ __host__ __device__ constexpr uint32_t pad_idx(uint32_t i) { return i + (i >> 4)
 // pad_idx(base + q*i) = pad_idx(base) + pad_off(q, i) for every (base, q, i) the passes below use (a group's base
 // has no bits between q and 16q resp. 4q, so nothing carries into the padding terms; scripts/check_stft_pad.py
 // enumerates all of them): one padded base per thread and compile-time offsets instead of two shifts per access
+// Pitch of one window's padded image (float2): with fewer than 16 threads per window a half warp spans several
+// windows, and its 64-bit accesses (thread lt of a window at 17*lt float2 plus a common offset) are free of bank
+// conflicts when the pitch is congruent to the team size modulo 16 (W = 64: 68 instead of 69, which put the
+// fourth window of a half warp on the banks of the first).  Pitch of one window's glyph row (bytes): W + 16, so
+// the byte stores of the 8 windows of a warp (W = 64) fall on different banks and rows stay 16-byte aligned.
+__host__ __device__ constexpr uint32_t win_pitch(uint32_t W)
+{
+    const uint32_t old = W + (W >> 4) + (W >> 8) + 1, tw = W / 16;
+    if (tw <= 1 || tw >= 16 || (W & 0x55555555u) == 0) return old; // one window per half warp (or thread), or log2 W odd
+    const uint32_t need = pad_idx(W - 1) + 1;
+    return need + ((tw + 16 - (need & 15)) & 15);
+}
+__host__ __device__ constexpr uint32_t glyph_pitch(uint32_t W) { return W + 16; }
 __host__ __device__ constexpr uint32_t pad_off(uint32_t q, uint32_t i) { return q * i + ((q * i) >> 4) + ((q * i) >> 8); }
 
 // base-4 digit reversal of x over nd digits
@@ -182,7 +195,7 @@ __global__ void __launch_bounds__(kStftThreads, MINB) fk_stft(const __grid_const
     constexpr int FIRST_BITS = ODD ? (LOGW >= 3 ? 3 : 1) : (LOGW >= 4 ? 4 : LOGW);
     constexpr int REST = LOGW - FIRST_BITS;                // log2 of what the later passes still combine
     constexpr int N16 = REST / 4, N4 = (REST % 4) / 2;
-    constexpr uint32_t WIN_SMEM = pad_idx(W) + 1;
+    constexpr uint32_t WIN_SMEM = win_pitch(W);
     constexpr uint32_t X_ELEMS = (WPC * WIN_SMEM + 1) & ~1u; // float2 elements, so the glyph rows start 16-byte aligned
     extern __shared__ __align__(16) float2 stft_smem[];
 
@@ -190,7 +203,7 @@ __global__ void __launch_bounds__(kStftThreads, MINB) fk_stft(const __grid_const
     const uint64_t u = static_cast<uint64_t>(blockIdx.x) * WPC + team;
     const bool active = u < a.n_units;
     float2 *x = stft_smem + static_cast<size_t>(team) * WIN_SMEM;
-    uint8_t *gl = reinterpret_cast<uint8_t *>(stft_smem + X_ELEMS) + static_cast<size_t>(team) * W; // the team's glyph row
+    uint8_t *gl = reinterpret_cast<uint8_t *>(stft_smem + X_ELEMS) + static_cast<size_t>(team) * glyph_pitch(W); // the team's glyph row
     const bool staged = !a.mag && a.use_thr; // index-only output: rows leave through shared memory, 16 bytes per thread
     const float2 *__restrict__ T = a.tw;
 
@@ -255,20 +268,15 @@ __global__ void __launch_bounds__(kStftThreads, MINB) fk_stft(const __grid_const
         __syncthreads();
         const bool last = (pass == N16 - 1) && N4 == 0;
         if (active) {
-            // one group of 16 per thread.  With q = 16 the blocks run along the lanes and k along the half warps:
-            // a warp then needs 2 values of every twiddle instead of 16 (its 15 twiddle loads were 240 L1
-            // wavefronts per pass at W = 4096), and the padded pitch of a block (273 float2) keeps the
-            // shared-memory accesses free of bank conflicts; other q keep k along the lanes.
-            const uint32_t NBLK = TW / q; // blocks of 16q points
-            const bool across = (q == 16) && NBLK > 1;
-            const uint32_t k = across ? lt / NBLK : (lt & (q - 1)), blk = across ? lt % NBLK : lt / q;
+            const uint32_t k = lt & (q - 1), blk = lt / q; // one group of 16 per thread
             const uint32_t base = blk * 16 * q + k;
             float2 *xb = x + pad_idx(base);
             float2 e[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) e[i] = xb[pad_off(q, i)];
             // the thread's 15 twiddles in order of use, [j][k] (stft_thread_twiddles): neighbouring k are neighbouring
-            // words, so a load is 1-2 lines per warp instead of up to 24 out of the natural table
+            // words, so a load is 1-2 lines per warp; out of the natural table a warp's 15 loads touched 240 lines
+            // in the q = 16 pass of W = 4096 and 96 in the q = 256 pass -- the L1 tag stage was the kernel's limiter
             const float2 *__restrict__ P = a.twp + (q - (1u << FIRST_BITS)); // 15 * (sum of q over the earlier passes)
             if (a.twp) levels2(e, k, q, a.one, [&](int j) { return __ldg(P + j * q + k); });
             else levels2(e, k, q, a.one, [&](int j) { return tw_natural(T, W, k, q, j); });
@@ -332,7 +340,7 @@ static int launch_stft_k(Chain &c, const FftArgs &fa, uint64_t units)
     constexpr uint32_t TW = W >= 16 ? W / 16 : 1;
     constexpr uint32_t WPC = kStftThreads / TW;
     constexpr int FIRST_BITS = (LOGW & 1) ? (LOGW >= 3 ? 3 : 1) : (LOGW >= 4 ? 4 : LOGW);
-    const size_t smem = LOGW == FIRST_BITS ? 0 : static_cast<size_t>((WPC * (pad_idx(W) + 1) + 1) & ~1u) * sizeof(float2) + static_cast<size_t>(WPC) * W;
+    const size_t smem = LOGW == FIRST_BITS ? 0 : static_cast<size_t>((WPC * win_pitch(W) + 1) & ~1u) * sizeof(float2) + static_cast<size_t>(WPC) * glyph_pitch(W);
     if (smem > 48 * 1024)
         QD_CUDA(cudaFuncSetAttribute(fk_stft<LOGW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const uint64_t grid = (units + WPC - 1) / WPC;
