@@ -29,9 +29,13 @@ __device__ __forceinline__ float2 padd(float2 a, float2 b) { return add2(a, b); 
 __device__ __forceinline__ float2 psub(float2 a, float2 b) { return fma2(b, make_float2(-1.0f, -1.0f), a); }
 __device__ __forceinline__ float2 pmul_tw(float2 a, float2 w, float2 one)
 {
-    const float2 p1 = mul2(make_float2(a.x, a.x), w);                      // (ax wx, ax wy)
-    const float2 p2 = mul2(make_float2(a.y, a.y), make_float2(-w.y, w.x)); // (-ay wy, ay wx)
-    return fma2(p2, one, p1);
+    // (ax wx - ay wy, ax wy + ay wx), each product and each sum rounded on its own.  The sign of the second
+    // product rides on the opaque constant, fl(ay (-wy)) = -fl(ay wy), and the halves of w are swapped by the
+    // operand's swizzle: no instruction builds (-wy, wx) (it was a negation and a move per twiddle, both on the
+    // FMA pipe that bounds fk_stft)
+    const float2 p1 = mul2(make_float2(a.x, a.x), w);                     // (ax wx, ax wy)
+    const float2 p2 = mul2(make_float2(a.y, a.y), make_float2(w.y, w.x)); // (ay wy, ay wx)
+    return fma2(p2, make_float2(-one.x, one.y), p1);
 }
 __device__ __forceinline__ void pradix4(float2 &t0, float2 &t1, float2 &t2, float2 &t3)
 {
