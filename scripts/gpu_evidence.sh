@@ -10,7 +10,7 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > $O/${TAG}_
 ( time python bench.py --steps 20 --warmup 5 ) > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; tail -c 300 $O/${TAG}_bench.err
 ( time python bench.py --impl reference --steps 5 --warmup 1 ) > $O/${TAG}_bench_ref.json 2>> $O/${TAG}_bench.err
 B="--steps 1 --warmup 1 --no-e2e --no-cpu-baseline"
-for item in cfg4:268435456:exact cfg1:67108864:exact cfg2:268435456:fast cfg2:268435456:exact cfg2s:268435456:exact cfg3:268435456:exact cfg5:268435456:exact; do
+for item in ${ITEMS:-cfg4:268435456:exact cfg1:67108864:exact cfg2:268435456:fast cfg2:268435456:exact cfg2s:268435456:exact cfg3:268435456:exact cfg5:268435456:exact}; do
   wl=$(echo $item | cut -d: -f1); S=$(echo $item | cut -d: -f2); P=$(echo $item | cut -d: -f3)
   A="--workload $wl --samples $S --precision $P $B"
   python bench.py $A > $O/${TAG}_plain_${wl}_$P.log 2>&1 &&

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """profiles/traffic.json from the ncu summaries of an evidence run (scripts/gpu_evidence.sh):
 
-    python scripts/make_traffic.py r2z
+    python scripts/make_traffic.py r2t r2v        # later tags override earlier ones, workload by workload
 
 For every workload: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels of ONE pass of the chain
 over the captured sample count, per input sample.  bench.py scales that to its own sample count.
@@ -12,9 +12,10 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-tag = sys.argv[1] if len(sys.argv) > 1 else "r2z"
+tags = sys.argv[1:] or ["r2z"]
 out = {}
-for f in sorted((ROOT / "profiles").glob(f"{tag}_full_*_summary.txt")):
+files = [(tag, f) for tag in tags for f in sorted((ROOT / "profiles").glob(f"{tag}_full_*_summary.txt"))]
+for tag, f in files:
     m = re.match(rf"{tag}_full_(\w+?)_(exact|fast)_summary", f.stem)
     if not m:
         continue

@@ -91,3 +91,27 @@ def test_tensor_core_fir_uses_tcgen05_tmem_and_the_bulk_copy_engine(built):
             assert mnemonic in text, (name, mnemonic)
         assert sum(x.startswith("UTCHMMA") or " UTCHMMA" in x for x in ins) >= 8, name  # K = 128 as eight K = 16 steps
         assert not any(re.search(r"I2F(P)?\.F16", x) for x in ins), name  # int8 -> f16 without conversion instructions
+
+
+def test_stft_glyphs_through_the_linear_form_and_no_twiddle_negations(built):
+    """fk_stft<12> (config 3): the epilogue decides glyphs from MUFU.SQRT + NaN-propagating clamps (qd_stft_epilogue.cuh
+    glyph_lin), and no FADD builds (-wy, wx) for the twiddle products any more (pmul_tw: the sign rides on the
+    constant operand of the FFMA2) -- both were FMA-pipe / issue costs that bounded the kernel."""
+    for name, _, ins in functions(built / "qd_stft.o"):
+        if "fk_stftILi12ELi4E" not in name:
+            continue
+        ops = [t.split()[1] if t.startswith("@") else t.split()[0] for t in ins]
+        assert sum(o.startswith("MUFU.SQRT") for o in ops) >= 16, "one square root per bin of a thread"
+        assert sum(o.startswith("FMNMX.NAN") for o in ops) >= 32
+        assert not any(re.match(r"FADD R\d+, -R\d+, -RZ", re.sub(r"^@!?P\d\s+", "", t)) for t in ins), "explicit negations are back"
+        return
+    raise AssertionError("fk_stft<12, 4> not found in qd_stft.o")
+
+
+def test_stft_padded_offsets_are_linear():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("check_stft_pad", ROOT / "scripts" / "check_stft_pad.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check() == 0
