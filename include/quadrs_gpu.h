@@ -145,7 +145,9 @@ int qd_chain_synchronize(qd_chain *c);
 /* Tuning knobs (tests and benches): "use_fast" 0/1 (0 forces the general unit-local executor), "fuse_stft" 0/1/2 (sparkfft inside the
  * filter kernel: never / back-to-back windows / also overlapping windows and two-stage chains),
  * "use_tc" 0/1 (FAST precision over cs8 captures: 1, the default, runs the filter on the tensor cores where the chain's shape allows;
- * 0 keeps the CUDA-core kernel), "segment_bytes" raw bytes staged per pipelined segment for host/file sources,
+ * 0 keeps the CUDA-core kernel), "glyph_lin" 0/1 (sparkfft bucket indices through the proven linear form of the square root
+ * where the range allows it: 1, the default; 0 keeps the per-glyph thresholds; results are identical),
+ * "segment_bytes" raw bytes staged per pipelined segment for host/file sources,
  * "scratch_budget" bytes of device scratch the general executor may use per batch. */
 int qd_chain_set_option(qd_chain *c, const char *key, int64_t value);
 
