@@ -127,6 +127,11 @@ __device__ __forceinline__ float2 div_exact2(float2 x, float den, float c)
     return fma2(r, c2, q0);
 }
 
+// cu8 / cs16 (lib.rs:252-253): fl(fl(x / den) - off) = fl(x * fl(1/den) - off) with ONE rounding, for every u8 / 255 and
+// every i16 / 65535 (exhaustive, exact rational arithmetic: tests/test_decode_trick.py) -- the result's ulp is so
+// much coarser than the quotient's that the first rounding never matters.  One packed FMA instead of four operations.
+__device__ __forceinline__ float2 dec_fused2(float2 x, float c, float off) { return fma2(x, make_float2(c, c), make_float2(off, off)); }
+
 // One sample of a 4-sample group held in w[] (FMT is compile time here)
 // SCALED = false (FAST mode, cs8): the integer value itself; the kernel's taps carry the 1/127
 template <int FMT, bool SCALED = true>
@@ -143,12 +148,12 @@ __device__ __forceinline__ float2 decode_in_group(const uint32_t (&w)[8], int i,
     if (FMT == QD_FMT_CU8) { // lib.rs:252: x/255 - 127.5 (the subtraction as q*1 + (-127.5), one rounding)
         const uint32_t h = w[i >> 1] >> ((i & 1) * 16);
         const float x = static_cast<float>(h & 0xff), y = static_cast<float>((h >> 8) & 0xff);
-        return fma2(div_exact2(make_float2(x, y), 255.0f, 1.0f / 255.0f), one, make_float2(-127.5f, -127.5f));
+        return dec_fused2(make_float2(x, y), 1.0f / 255.0f, -127.5f);
     }
     // cs16, lib.rs:253
     const float x = static_cast<float>(static_cast<int>(static_cast<short>(w[i] & 0xffff)));
     const float y = static_cast<float>(static_cast<int>(static_cast<short>(w[i] >> 16)));
-    return fma2(div_exact2(make_float2(x, y), 65535.0f, 1.0f / 65535.0f), one, make_float2(-32767.5f, -32767.5f));
+    return dec_fused2(make_float2(x, y), 1.0f / 65535.0f, -32767.5f);
 }
 
 // ---------------------------------------------------------------------------- tile geometry
@@ -522,7 +527,7 @@ __device__ __forceinline__ void unpack_words(const uint32_t (&raw)[4], float2 (&
         for (int i = 0; i < 4; i++) {
             const float2 n = add2(make_float2(__uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7410)),
                                               __uint_as_float(__byte_perm(w[i], 0x4B000000u, 0x7432))), negk);
-            x[i] = fma2(div_exact2(n, 65535.0f, 1.0f / 65535.0f), one, make_float2(-32767.5f, -32767.5f)); // lib.rs:253
+            x[i] = dec_fused2(n, 1.0f / 65535.0f, -32767.5f); // lib.rs:253
         }
     } else {
         const uint32_t flip = FMT == QD_FMT_CS8 ? 0x80808080u : 0u;
@@ -536,7 +541,7 @@ __device__ __forceinline__ void unpack_words(const uint32_t (&raw)[4], float2 (&
             const float2 n = add2(make_float2(__uint_as_float(__byte_perm(word, 0x4B000000u, sel)),
                                               __uint_as_float(__byte_perm(word, 0x4B000000u, sel + 1))), negk);
             if (FMT == QD_FMT_CS8) x[i] = div_exact2(n, 127.0f, 1.0f / 127.0f); // lib.rs:251
-            else x[i] = fma2(div_exact2(n, 255.0f, 1.0f / 255.0f), one, make_float2(-127.5f, -127.5f)); // lib.rs:252
+            else x[i] = dec_fused2(n, 1.0f / 255.0f, -127.5f); // lib.rs:252
         }
     }
 }
