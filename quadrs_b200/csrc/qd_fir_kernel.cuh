@@ -581,9 +581,10 @@ __device__ __forceinline__ void mix_group_exact(const FirArgs &a, float2 (&x)[4]
 // the next group's load in flight while the current one is decoded and mixed.
 template <class Gm, int STRIDE, int FMT>
 __device__ __forceinline__ void decode_exact_global(const FirArgs &a, const uint8_t *__restrict__ g0, uint32_t n_dec, uint64_t n0,
-                                                    float4 *__restrict__ X4, int idx)
+                                                    float4 *__restrict__ X4, int idx, uint32_t g_first = 0)
 {
     static_assert(STRIDE % Gm::G == 0, "a thread's groups stay in one row");
+    idx += static_cast<int>(g_first); // groups below g_first are already in place (carried over from the CTA's previous tile)
     constexpr uint32_t GB = FMT == QD_FMT_CF32 ? 32u : (FMT == QD_FMT_CS16 ? 16u : 8u); // bytes per group of 4 samples
     // integer formats: a partial last group is decoded whole (its bytes lie inside the 16-byte granule the source
     // contract makes readable); cf32 groups are two granules, so the last 0..3 samples go one at a time
@@ -1396,6 +1397,27 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         t_step = 1;
         if (t_first >= t_last) t_begin = t_last; // no tile for this CTA
     }
+    // CARRY (long run-time-length filters over unstaged integer tiles, config 4's shape): consecutive tiles overlap
+    // by L - D samples, a tenth of a tile at L = 800, D = 16, and decode + f64 mixer are 40 % of such a tile's time.
+    // A CTA therefore walks a contiguous run of tiles and moves the overlap -- the last L - D decoded and mixed
+    // samples, which are the next tile's first -- across in registers (the same row of the polyphase layout,
+    // T_TILE*D/DR columns to the left) instead of decoding and mixing it again.  Values are pure functions of the
+    // absolute sample index, so nothing changes bit for bit.
+    constexpr bool CARRY = EXACT && LS == 0 && FUSE <= 1;
+    constexpr uint32_t CARRY_MAX = 4; // float4 per thread held across the STFT
+    constexpr uint32_t SHIFT_COLS = static_cast<uint32_t>(Gm::T_TILE) * D / Gm::DR;
+    const uint32_t ov_groups = (a.L > static_cast<uint32_t>(D) && ((a.L - D) & 3) == 0) ? (a.L - D) / 4 : 0;
+    const uint32_t span_full = static_cast<uint32_t>(Gm::T_TILE - 1) * D + a.L;
+    const bool carry_run = CARRY && !staged && a.fmt != QD_FMT_CF32 && a.contiguous && ov_groups != 0 &&
+                           2 * ov_groups <= CARRY_MAX * NT && (Gm::T_TILE * D) % Gm::DR == 0 && a.n_tiles > gridDim.x;
+    if (CARRY && carry_run) {
+        const uint64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
+        t_first = t_begin = blockIdx.x * per;
+        t_last = min(t_first + per, a.n_tiles);
+        t_step = 1;
+        if (t_first >= t_last) t_begin = t_last; // no tile for this CTA
+    }
+    bool have_carry = false;
     uint64_t it = 0;
     if (tid == 0 && t_begin < t_last) issue(tile_geo<D, Gm::T_TILE>(a, t_begin));
 
@@ -1410,6 +1432,7 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         if (staged) mbar_wait(&mbar[0], static_cast<uint32_t>(it & 1));
 
         // ---- decode + mix once per sample, into the polyphase layout ------------------------------
+        bool decoded_lean = false; // through decode_exact_global from local sample 0 on: the whole span is in X
         {
             const uint8_t *raw = staged ? raw0 : reinterpret_cast<const uint8_t *>(gbeg & ~uintptr_t(15));
             if (!EXACT && lean && (lead & 3) == 0 && (!lean_mix || lphase->ok)) {
@@ -1423,11 +1446,13 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
             } else if (EXACT && !staged && a.fmt != QD_FMT_CF32 && (lead & 3) == 0 && l_lo == 0) {
                 const uint8_t *g0 = raw + pb * lead;
                 float4 *X4 = reinterpret_cast<float4 *>(X);
+                const uint32_t gf = (CARRY && have_carry) ? ov_groups : 0u; // the overlap is already in place
                 switch (a.fmt) {
-                case QD_FMT_CS8: decode_exact_global<Gm, NT, QD_FMT_CS8>(a, g0, n_dec, g.n_tile0, X4, tid); break;
-                case QD_FMT_CU8: decode_exact_global<Gm, NT, QD_FMT_CU8>(a, g0, n_dec, g.n_tile0, X4, tid); break;
-                default: decode_exact_global<Gm, NT, QD_FMT_CS16>(a, g0, n_dec, g.n_tile0, X4, tid); break;
+                case QD_FMT_CS8: decode_exact_global<Gm, NT, QD_FMT_CS8>(a, g0, n_dec, g.n_tile0, X4, tid, gf); break;
+                case QD_FMT_CU8: decode_exact_global<Gm, NT, QD_FMT_CU8>(a, g0, n_dec, g.n_tile0, X4, tid, gf); break;
+                default: decode_exact_global<Gm, NT, QD_FMT_CS16>(a, g0, n_dec, g.n_tile0, X4, tid, gf); break;
                 }
+                decoded_lean = true;
             } else if (EXACT && staged && (lead & 3) == 0 && l_lo == 0) {
                 const uint32_t raw_addr = smem_u32(raw) + pb * lead;
                 float4 *X4 = reinterpret_cast<float4 *>(X);
@@ -1464,10 +1489,35 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         uint32_t snap_mask;
         const bool mine = fir_tile<D, R, NT, LMAX, EXACT, LS, SNAP, FUSE>(a, taps, g, X, tid, tid, acc, snapv, snap_mask);
         __syncthreads();
+        // the overlap with the CTA's next tile leaves X before the STFT reuses its first bytes
+        float4 cr[CARRY_MAX];
+        const bool carry_next = CARRY && carry_run && decoded_lean && n_dec == span_full && tile + 1 < t_last;
+        auto carry_slot = [&](uint32_t e) { // element e of the overlap: group e (first halves), then group e - ov_groups (second halves)
+            const uint32_t half = e >= ov_groups ? 1u : 0u, gq = e - half * ov_groups;
+            return ((gq & (Gm::G - 1)) + half * Gm::G) * Gm::PITCH + (gq >> Gm::LOG_G);
+        };
+        if (CARRY && carry_next) {
+            const float4 *X4 = reinterpret_cast<const float4 *>(X);
+#pragma unroll
+            for (uint32_t j = 0; j < CARRY_MAX; j++) {
+                const uint32_t e = tid + j * NT;
+                if (e < 2 * ov_groups) cr[j] = X4[carry_slot(e) + SHIFT_COLS];
+            }
+        }
         if constexpr (FUSE == 1) {
             fused_stft<R, NT, Gm::T_TILE>(a, g, X, acc, mine, tid); // X is free: every thread has left the filter
             __syncthreads();
-        } else if constexpr (FUSE == 2) {
+        }
+        if (CARRY && carry_next) { // disjoint from what the next decode writes (groups >= ov_groups); it ends with a barrier
+            float4 *X4 = reinterpret_cast<float4 *>(X);
+#pragma unroll
+            for (uint32_t j = 0; j < CARRY_MAX; j++) {
+                const uint32_t e = tid + j * NT;
+                if (e < 2 * ov_groups) X4[carry_slot(e)] = cr[j];
+            }
+        }
+        have_carry = carry_next;
+        if constexpr (FUSE == 2) {
             fused_stream_stft<R, NT, Gm::T_TILE>(a, g, X, reinterpret_cast<float2 *>(smem + a.carry_off), acc, snapv, snap_mask, mine,
                                                  tile < t_first, tid);
             __syncthreads();

@@ -654,3 +654,36 @@ def test_full_size_config5_whole_buffer(Q):
     rows = _full_size_sparkfft(Q, Q.CF32, rate, 2**32, st, 4, 2, (0.001, 0.01), synth, (4 * 32 + 40) * 8 + 40,
                                [0, 1, 2, 4_194_303, 4_194_304, -2, -1])
     assert rows > 8_000_000
+
+
+@pytest.mark.parametrize("fmt,stages,sink", [
+    (O.CS16, [("shift", 7_000_000), ("lowpass", 2_000_000, 16, 800)], ("spark", 128, 128, (0.5, 50.0))),   # config 4: FUSE = 1
+    (O.CU8, [("shift", -3_000_000), ("lowpass", 1_500_000, 16, 404)], ("write", 0x1000)),                    # no STFT in the kernel
+    (O.CS8, [("shift", 1_000_000), ("shift", 250_000), ("lowpass", 900_000, 32, 800)], ("spark", 64, 64, (0.05, 2.0))),
+])
+def test_overlap_carried_between_consecutive_tiles(Q, fmt, stages, sink):
+    """Long run-time-length filters over integer captures (fk_fir CARRY): a CTA walks a contiguous run of tiles and
+    moves the L - D overlapping, already mixed samples across in registers instead of decoding them again.  With one
+    CTA per SM and a capture of a few hundred tiles every CTA carries (runs of 2 - 3 tiles); every output against the
+    oracle and against the general executor, bit for bit -- and against the same chain cut differently (two more
+    CTAs per SM: other tiles are run-first)."""
+    D = stages[-1][2]
+    tile_samples = (512 if D == 16 else 256) * D
+    n = 330 * tile_samples + 12_345
+    raw, _ = synth_raw(fmt, n, rate=100e6)
+    fused = gpu_chain(raw, fmt, 100_000_000, stages).set_option("fir_cta_cap", 1)
+    other = gpu_chain(raw, fmt, 100_000_000, stages).set_option("fir_cta_cap", 3)
+    general = gpu_chain(raw, fmt, 100_000_000, stages).set_option("use_fast", 0)
+    got, rc = _run(fused, sink)
+    alt, rc1 = _run(other, sink)
+    ref, rc2 = _run(general, sink)
+    with kept_only():
+        want, rc3 = _run_oracle(oracle_chain(raw, fmt, 100_000_000, stages), sink)
+    assert rc == rc1 == rc2 == rc3
+    if sink[0] == "write":
+        assert_bit_equal(got, want, "carried tiles vs oracle")
+        assert_bit_equal(alt, want, "other run lengths vs oracle")
+        assert_bit_equal(ref, want, "general executor vs oracle")
+    else:
+        assert np.array_equal(got[0], want[0]) and np.array_equal(alt[0], want[0]) and np.array_equal(ref[0], want[0])
+        assert_bit_equal(got[1], want[1], "magnitudes, carried tiles vs oracle")
