@@ -147,7 +147,8 @@ int qd_chain_synchronize(qd_chain *c);
  * "use_tc" 0/1 (FAST precision over cs8 captures: 1, the default, runs the filter on the tensor cores where the chain's shape allows;
  * 0 keeps the CUDA-core kernel), "glyph_lin" 0/1 (sparkfft bucket indices through the proven linear form of the square root
  * where the range allows it: 1, the default; 0 keeps the per-glyph thresholds; results are identical),
- * "segment_bytes" raw bytes staged per pipelined segment for host/file sources,
+ * "fir_carry" 0/1 (long filters: a CTA carries the samples two consecutive tiles share instead of decoding them twice: 1, the
+ * default; results are identical), "segment_bytes" raw bytes staged per pipelined segment for host/file sources,
  * "scratch_budget" bytes of device scratch the general executor may use per batch. */
 int qd_chain_set_option(qd_chain *c, const char *key, int64_t value);
 

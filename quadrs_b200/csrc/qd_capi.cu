@@ -319,6 +319,7 @@ int qd_chain_set_option(qd_chain *c, const char *key, int64_t value)
     else if (!strcmp(key, "glyph_lin") && value >= 0 && value <= 1) c->glyph_lin = static_cast<int>(value);
     else if (!strcmp(key, "stft_minb") && value >= 2 && value <= 4) c->stft_minb = static_cast<int>(value);
     else if (!strcmp(key, "fir_cta_cap") && value >= 0) c->fir_cta_cap = static_cast<int>(value);
+    else if (!strcmp(key, "fir_carry") && value >= 0 && value <= 1) c->fir_carry = static_cast<int>(value);
     else if (!strcmp(key, "segment_bytes") && value > 0) c->segment_bytes = static_cast<size_t>(value);
     else if (!strcmp(key, "scratch_budget") && value > 0) c->scratch_budget = static_cast<size_t>(value);
     else return set_error(QD_E_INVALID_ARG, "unknown option %s=%lld", key, (long long)value);

@@ -252,6 +252,7 @@ static int launch_fir(Chain &c, const LpInfo &lp, int fmt, int n_shift, const do
     // units that tile the output stream are filtered as ONE stream cut into absolute tiles; a thread's R outputs
     // must then never straddle a unit boundary (off0 and n_call multiples of R)
     a.contiguous = (n_units == 1 || (S == n_call && off0 % R == 0 && n_call % R == 0)) ? 1 : 0;
+    a.no_carry = c.fir_carry ? 0 : 1;
     a.ncall_log2 = -1;
     if (is_pow2(n_call))
         for (int b = 0; b < 64; b++)

@@ -53,6 +53,7 @@ struct FirArgs {
     uint64_t S;          // unit stride in top-level samples
     uint64_t n_units;
     int contiguous; // S == n_call: the units tile the output stream
+    int no_carry;   // experiments: 1 = every tile decodes its whole span (no overlap carried between a CTA's consecutive tiles)
     uint32_t tiles_per_unit;
     uint64_t n_tiles;
     uint64_t tile_first; // contiguous mode: tiles are numbered from ABSOLUTE top-level output 0 (tile A holds outputs
@@ -584,6 +585,7 @@ __device__ __forceinline__ void decode_exact_global(const FirArgs &a, const uint
                                                     float4 *__restrict__ X4, int idx, uint32_t g_first = 0)
 {
     static_assert(STRIDE % Gm::G == 0, "a thread's groups stay in one row");
+    const bool first_thread = idx == 0;
     idx += static_cast<int>(g_first); // groups below g_first are already in place (carried over from the CTA's previous tile)
     constexpr uint32_t GB = FMT == QD_FMT_CF32 ? 32u : (FMT == QD_FMT_CS16 ? 16u : 8u); // bytes per group of 4 samples
     // integer formats: a partial last group is decoded whole (its bytes lie inside the 16-byte granule the source
@@ -630,7 +632,7 @@ __device__ __forceinline__ void decode_exact_global(const FirArgs &a, const uint
         xb[0] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
         xb[Gm::G * Gm::PITCH] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
     }
-    if (FMT == QD_FMT_CF32 && idx == 0) { // the last 0..3 samples, one at a time
+    if (FMT == QD_FMT_CF32 && first_thread) { // the last 0..3 samples, one at a time
         for (uint32_t l = 4 * n_loc; l < n_dec; l++) {
             float2 v = __ldg(reinterpret_cast<const float2 *>(g0) + l);
             const double ni = __ull2double_rn(n0 + l);
@@ -1397,7 +1399,8 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
         t_step = 1;
         if (t_first >= t_last) t_begin = t_last; // no tile for this CTA
     }
-    // CARRY (long run-time-length filters over unstaged integer tiles, config 4's shape): consecutive tiles overlap
+    // CARRY (long run-time-length filters over unstaged tiles -- integer formats, cf32 behind a shift: configs 4 and 1):
+    // consecutive tiles overlap
     // by L - D samples, a tenth of a tile at L = 800, D = 16, and decode + f64 mixer are 40 % of such a tile's time.
     // A CTA therefore walks a contiguous run of tiles and moves the overlap -- the last L - D decoded and mixed
     // samples, which are the next tile's first -- across in registers (the same row of the polyphase layout,
@@ -1408,7 +1411,7 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
     constexpr uint32_t SHIFT_COLS = static_cast<uint32_t>(Gm::T_TILE) * D / Gm::DR;
     const uint32_t ov_groups = (a.L > static_cast<uint32_t>(D) && ((a.L - D) & 3) == 0) ? (a.L - D) / 4 : 0;
     const uint32_t span_full = static_cast<uint32_t>(Gm::T_TILE - 1) * D + a.L;
-    const bool carry_run = CARRY && !staged && a.fmt != QD_FMT_CF32 && a.contiguous && ov_groups != 0 &&
+    const bool carry_run = CARRY && !a.no_carry && !staged && (a.fmt != QD_FMT_CF32 || a.n_shift != 0) && a.contiguous && ov_groups != 0 &&
                            2 * ov_groups <= CARRY_MAX * NT && (Gm::T_TILE * D) % Gm::DR == 0 && a.n_tiles > gridDim.x;
     if (CARRY && carry_run) {
         const uint64_t per = (a.n_tiles + gridDim.x - 1) / gridDim.x;
@@ -1442,7 +1445,9 @@ __global__ void __launch_bounds__(NT, (ctas_per_sm<D, R, NT, EXACT, LS>())) fk_f
                 decode_cf32_copy<Gm, NT>(raw, n_dec, X, tid);
             } else if (EXACT && a.fmt == QD_FMT_CF32 && lead == 0 && l_lo == 0) {
                 // cf32 behind shifts: the same lean loop as the unstaged integer tiles (packed mixer, next group in flight)
-                decode_exact_global<Gm, NT, QD_FMT_CF32>(a, raw, n_dec, g.n_tile0, reinterpret_cast<float4 *>(X), tid);
+                decode_exact_global<Gm, NT, QD_FMT_CF32>(a, raw, n_dec, g.n_tile0, reinterpret_cast<float4 *>(X), tid,
+                                                         (CARRY && have_carry) ? ov_groups : 0u);
+                decoded_lean = true;
             } else if (EXACT && !staged && a.fmt != QD_FMT_CF32 && (lead & 3) == 0 && l_lo == 0) {
                 const uint8_t *g0 = raw + pb * lead;
                 float4 *X4 = reinterpret_cast<float4 *>(X);

@@ -164,6 +164,7 @@ struct Chain {
     std::vector<uint8_t> tc_host; // its host copy (source of the upload)
     uint64_t tc_key[4] = {0, 0, 0, 0}; // (L, D, bits of the ratio sum, tap checksum) the image was built for
     float tc_s_hi = 0.0f, tc_s_lo = 0.0f;
+    int fir_carry = 1;   // fk_fir: carry the overlap between a CTA's consecutive tiles (long filters); 0 = experiments
     int fir_cta_cap = 0; // experiments: resident fk_fir CTAs per SM (0 = as many as fit)
     size_t segment_bytes = size_t(32) << 20; // raw bytes staged per segment for host / file sources (measured best of 16..256 MiB)
     bool pipeline_ready = false;

@@ -660,6 +660,7 @@ def test_full_size_config5_whole_buffer(Q):
     (O.CS16, [("shift", 7_000_000), ("lowpass", 2_000_000, 16, 800)], ("spark", 128, 128, (0.5, 50.0))),   # config 4: FUSE = 1
     (O.CU8, [("shift", -3_000_000), ("lowpass", 1_500_000, 16, 404)], ("write", 0x1000)),                    # no STFT in the kernel
     (O.CS8, [("shift", 1_000_000), ("shift", 250_000), ("lowpass", 900_000, 32, 800)], ("spark", 64, 64, (0.05, 2.0))),
+    (O.CF32, [("shift", 1_300_000), ("lowpass", 900_000, 32, 400)], ("spark", 64, 16, (0.05, 2.0))),        # config 1's shape: snapshots
 ])
 def test_overlap_carried_between_consecutive_tiles(Q, fmt, stages, sink):
     """Long run-time-length filters over integer captures (fk_fir CARRY): a CTA walks a contiguous run of tiles and
